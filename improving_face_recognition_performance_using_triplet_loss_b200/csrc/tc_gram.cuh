@@ -1,0 +1,343 @@
+// tc_gram.cuh -- the tcgen05 / TMEM / TMA Gram mainloop shared by the batch-hard mining kernel,
+// the gallery top-k kernel and the all-pairs cosine kernel (sm_100a only).
+//
+//   G[i][j] = sum_k A[i][k] * B[j][k]      A: (M, Kp) bf16, B: (N, Kp) bf16, both K-major, fp32 accumulate
+//
+// One CTA = 10 warps: warps 0-7 epilogue (warp w reads TMEM lane quarter w%4, column half w/4),
+// warp 8 TMA producer (one elected lane), warp 9 MMA issuer (one elected lane) + TMEM owner.
+// Tile = 128 rows x 256 columns x K (UMMA M=128, N=256, K=16, cta_group::1), accumulator
+// double-buffered in TMEM (2 x 256 columns = all 512), so the epilogue of tile t overlaps the MMAs of
+// tile t+1.  The A row-block (128 x Kp) stays resident in shared memory while the CTA walks its
+// column tiles; B streams through a ring of 32 KB K-block stages (256 rows x 64 bf16, SWIZZLE_128B).
+// The Gram tile never leaves the SM: the epilogue functor consumes it 32 columns at a time straight
+// from TMEM registers.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace efm {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int A_KB_BYTES = BM * BK * 2;   // 16 KB per K-block of the resident A row-block
+constexpr int B_ST_BYTES = BN * BK * 2;   // 32 KB per B stage
+constexpr int EPI_WARPS = 8;
+constexpr int PRODUCER_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int THREADS = 320;
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_NK = 8;                 // K <= 512
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_LIMIT = 232448;        // 227 KB opt-in maximum per CTA
+
+struct GramParams {
+  int M, N;              // valid rows of A / rows of B (= Gram columns)
+  int nk;                // K blocks of 64 (Kp = 64 * nk)
+  int stages;            // B ring depth
+  int row_blocks, col_tiles;
+  int sched_mode;        // 0: contiguous tile ranges over the whole grid; 1: `splits` CTAs per row block
+  int splits;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (it == 64) t0 = clock64();
+    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) {   // ~2 s
+      printf("efmtl: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tiled TMA load global -> shared, completion on an mbarrier (c0 = innermost coordinate)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+constexpr uint64_t SMEM_DESC_BASE = (uint64_t(1) << 16)              // leading byte offset (unused for SW128 K-major)
+                                    | (uint64_t(1024 >> 4) << 32)    // stride byte offset between 8-row groups
+                                    | (uint64_t(1) << 46)            // descriptor version 1 (sm_100)
+                                    | (uint64_t(2) << 61);           // SWIZZLE_128B
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) { return SMEM_DESC_BASE | uint64_t((addr & 0x3FFFFu) >> 4); }
+
+// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, N=256, M=128
+constexpr uint32_t IDESC_BF16_M128_N256 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when they complete
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread t gets lane base+t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- tile schedule -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_range(const GramParams& g, long& t0, long& t1) {
+  const long CT = g.col_tiles;
+  if (g.sched_mode == 0) {
+    const long T = (long)g.row_blocks * CT, G = gridDim.x, c = blockIdx.x;
+    t0 = c * T / G;
+    t1 = (c + 1) * T / G;
+  } else {
+    const long rb = blockIdx.x / g.splits, s = blockIdx.x % g.splits;
+    t0 = rb * CT + s * CT / g.splits;
+    t1 = rb * CT + (s + 1) * CT / g.splits;
+  }
+}
+
+inline size_t smem_bytes(int nk, int stages, int extra) {
+  return 1024 /*alignment slack*/ + (size_t)nk * A_KB_BYTES + (size_t)stages * B_ST_BYTES + 256 /*barriers*/ + extra;
+}
+inline int pick_stages(int nk, int extra) {
+  int s = (int)((SMEM_LIMIT - 1024 - 256 - extra - (long)nk * A_KB_BYTES) / B_ST_BYTES);
+  return s > MAX_STAGES ? MAX_STAGES : s;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+// Epi supplies:  struct Params;  struct State;
+//   static __device__ void row_begin(const Params&, const GramParams&, int row, State&);
+//   static constexpr int SMEM_PER_WARP;   (bytes of scratch shared memory per epilogue warp, may be 0)
+//   static __device__ void chunk(const Params&, const GramParams&, State&, int row, const uint32_t (&acc)[32], int col0,
+//                                float* scratch);
+//   static __device__ void row_end(const Params&, const GramParams&, int row, int part, State&);
+// row = anchor/query row index of this thread, col0 = first Gram column of the 32-column chunk held in
+// acc (fp32 bit patterns); part = ordinal of (CTA, column half) for partial-result slots.
+template <class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams g,
+            const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t sA = base;
+  const uint32_t sB = sA + (uint32_t)g.nk * A_KB_BYTES;
+  const uint32_t sBar = sB + (uint32_t)g.stages * B_ST_BYTES;
+  // barrier slots (8 B each)
+  const uint32_t bar_full = sBar;                       // [MAX_STAGES]
+  const uint32_t bar_empty = sBar + 8 * MAX_STAGES;     // [MAX_STAGES]
+  const uint32_t bar_a_full = sBar + 16 * MAX_STAGES;
+  const uint32_t bar_a_empty = bar_a_full + 8;
+  const uint32_t bar_acc_full = bar_a_empty + 8;        // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;     // [2]
+  const uint32_t tmem_slot = bar_acc_empty + 16;        // u32
+  float* scratch = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw))) +
+                   (threadIdx.x >> 5) * (Epi::SMEM_PER_WARP / 4);   // epilogue warps are warps 0..7
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_empty, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + 8 * a, 1); mbar_init(bar_acc_empty + 8 * a, EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == PRODUCER_WARP && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  long t0, t1;
+  tile_range(g, t0, t1);
+  const int CT = g.col_tiles;
+
+  if (warp == PRODUCER_WARP) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, a_empty_phase = 0; int cur_rb = -1;
+      for (long t = t0; t < t1; ++t) {
+        const int rb = (int)(t / CT), ct = (int)(t % CT);
+        if (rb != cur_rb) {
+          if (cur_rb >= 0) { mbar_wait(bar_a_empty, a_empty_phase); a_empty_phase ^= 1; }
+          mbar_expect_tx(bar_a_full, (uint32_t)g.nk * A_KB_BYTES);
+          for (int kb = 0; kb < g.nk; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, bar_a_full, kb * BK, rb * BM);
+          cur_rb = rb;
+        }
+        for (int kb = 0; kb < g.nk; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * stage, B_ST_BYTES);
+          tma_load_2d(sB + stage * B_ST_BYTES, &tmB, bar_full + 8 * stage, kb * BK, ct * BN);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, a_full_phase = 0; int cur_rb = -1;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long t = t0; t < t1; ++t) {
+        const int rb = (int)(t / CT);
+        mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);           // epilogue drained this accumulator
+        tc_fence_after();
+        if (rb != cur_rb) { mbar_wait(bar_a_full, a_full_phase); a_full_phase ^= 1; cur_rb = rb; }
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < g.nk; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a0 = sA + kb * A_KB_BYTES, b0 = sB + stage * B_ST_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, smem_desc(a0 + k * 32), smem_desc(b0 + k * 32), IDESC_BF16_M128_N256, (kb | k) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * stage);                        // stage reusable once these MMAs retire
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_acc_full + 8 * acc);                         // accumulator ready for the epilogue
+        const bool last_of_rb = (t + 1 == t1) || ((int)((t + 1) / CT) != rb);
+        if (last_of_rb) umma_commit(bar_a_empty);                    // A row-block may be overwritten
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps ----------------
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int acc = 0; uint32_t acc_phase = 0; int cur_rb = -1;
+    typename Epi::State st;
+    int row = 0;
+    const int part = (int)blockIdx.x * 2 + half;
+    for (long t = t0; t < t1; ++t) {
+      const int rb = (int)(t / CT), ct = (int)(t % CT);
+      if (rb != cur_rb) {
+        if (cur_rb >= 0) Epi::row_end(ep, g, row, part, st);
+        row = rb * BM + quarter * 32 + lane;
+        Epi::row_begin(ep, g, row, st);
+        cur_rb = rb;
+      }
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * BN + half * (BN / 2));
+#pragma unroll 1
+      for (int c = 0; c < BN / 2 / 32; ++c) {
+        const int col0 = ct * BN + half * (BN / 2) + c * 32;
+        if (col0 >= g.N) break;                                      // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_acc + c * 32, v);
+        tmem_ld_wait();
+        Epi::chunk(ep, g, st, row, v, col0, scratch);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (cur_rb >= 0) Epi::row_end(ep, g, row, part, st);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == MMA_WARP) { __syncwarp(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---- host side: tensor maps + launch ----------------------------------------------------------------------
+// 2-D bf16 row-major (rows, Kp) tensor map with a (64 x box_rows) box, SWIZZLE_128B, zero OOB fill.
+int make_tmap_bf16(CUtensorMap* out, const void* base, long rows, long Kp, int box_rows);
+
+template <class Epi>
+int launch_gram(const void* A, const void* B, GramParams g, const typename Epi::Params& ep, int grid, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, g.N, (long)g.nk * BK, BN);
+  if (rc) return rc;
+  const size_t smem = smem_bytes(g.nk, g.stages, Epi::SMEM_PER_WARP * EPI_WARPS);
+  static bool attr_done = false;                                     // per instantiation
+  if (!attr_done) {
+    EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_done = true;
+  }
+  gram_kernel<Epi><<<grid, THREADS, smem, st>>>(tmA, tmB, g, ep);
+  EFM_LAUNCH_CHECK("gram_kernel");
+  return EFM_OK;
+}
+
+// fills row_blocks / col_tiles / stages / schedule and returns the grid size
+inline int plan_gram(GramParams& g, int sched_mode, int smem_extra = 0) {
+  g.row_blocks = (int)cdiv(g.M, BM);
+  g.col_tiles = (int)cdiv(g.N, BN);
+  g.stages = pick_stages(g.nk, smem_extra);
+  g.sched_mode = sched_mode;
+  const long T = (long)g.row_blocks * g.col_tiles;
+  const int sms = num_sms();
+  if (sched_mode == 0) {
+    g.splits = 1;
+    return (int)(T < sms ? T : sms);
+  }
+  // mode 1: every row block is cut into `splits` column ranges so that the grid covers the SMs
+  int splits = (int)cdiv(2L * sms, g.row_blocks);                    // ~2 CTAs per SM over the run
+  if (splits > g.col_tiles) splits = g.col_tiles;
+  if (splits < 1) splits = 1;
+  g.splits = splits;
+  return g.row_blocks * splits;
+}
+
+}  // namespace tc
+}  // namespace efm

@@ -1,0 +1,62 @@
+"""Multi-GPU forms of the two paths that have a real exchange step.
+
+* global batch-hard mining: all-gather of embeddings + labels (NCCL over NVLink on GPUs, gloo in CPU tests of
+  the host logic), every rank mines its B/P x B strip against the global batch; row extrema are complete per
+  rank, so mining needs no reduction.  Exact mode reduce-scatters dE_all so the result equals the single-GPU
+  loss on the concatenated batch; detached mode (reference-faithful, negatives are constants) needs no
+  backward collective.
+* sharded gallery top-k: each rank owns a contiguous row shard, local top-k with global indices, all-gather of
+  (score, idx) lists and a K-way merge on every rank.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of n rows for `rank` (first n % world shards one row longer)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate equally-sized row blocks of all ranks (rank order)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def global_batch_hard(E_local: torch.Tensor, labels_local: torch.Tensor, margin: float, *, normalize=True,
+                      exact_grad=True, mine_bf16=None, group=None, _impl=None):
+    """Batch-hard triplet loss over the global batch.  Returns (loss_local (B,), idx_p, idx_n (global row
+    indices), dE_local (B, D) fp32).  `_impl` lets the CPU tests substitute the single-process operator."""
+    from .loss import batch_hard_triplet
+    impl = _impl or batch_hard_triplet
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B = E_local.shape[0]
+    E_all = all_gather_rows(E_local, group)
+    y_all = all_gather_rows(labels_local.reshape(-1).to(torch.int32), group)
+    loss, idx_p, idx_n, dE_all = impl(E_all, y_all, margin, normalize=normalize, row_offset=rank * B, num_local=B,
+                                      want_grad=True, detach_gathered=not exact_grad, mine_bf16=mine_bf16)
+    if exact_grad and world > 1:
+        dE_local = torch.empty((B, E_local.shape[1]), dtype=dE_all.dtype, device=dE_all.device)
+        dist.reduce_scatter_tensor(dE_local, dE_all.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    else:
+        dE_local = dE_all[rank * B:(rank + 1) * B]
+    return loss, idx_p, idx_n, dE_local
+
+
+def sharded_topk(local_scores: torch.Tensor, local_idx: torch.Tensor, group=None, _merge=None):
+    """All-gather per-shard (nq, K) lists (indices already global) and merge -> (nq, K) on every rank."""
+    from .gallery import merge_topk
+    merge = _merge or merge_topk
+    world = dist.get_world_size(group)
+    nq, K = local_scores.shape
+    ps = torch.empty((world, nq, K), dtype=local_scores.dtype, device=local_scores.device)
+    pi = torch.empty((world, nq, K), dtype=local_idx.dtype, device=local_idx.device)
+    dist.all_gather_into_tensor(ps, local_scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(pi, local_idx.contiguous(), group=group)
+    return merge(ps, pi)
