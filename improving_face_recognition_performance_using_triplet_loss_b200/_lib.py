@@ -46,6 +46,7 @@ SIGNATURES = {
     "efm_cosine_allpairs": (_i, [_vp, _vp, _l, _l, _l, _i, _vp, _vp, _sz, _vp]),
     "efm_bh_workspace_bytes": (_sz, [_l, _l, _l, _i, _i]),
     "efm_bh_triplet_fwd_bwd": (_i, [_vp, _vp, _l, _l, _l, _l, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "efm_bh_mine": (_i, [_vp, _l, _l, _l, _l, _i, _i, _vp, _sz, _vp]),
     "efm_bh_backward_workspace_bytes": (_sz, [_l]),
     "efm_bh_backward": (_i, [_vp, _l, _l, _l, _l, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "efm_gallery_scores_f32": (_i, [_vp, _vp, _l, _l, _vp, _l, _vp, _vp]),

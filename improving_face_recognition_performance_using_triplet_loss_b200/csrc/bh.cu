@@ -327,6 +327,36 @@ bh_norm_bwd_kernel(const T* __restrict__ E, const float* __restrict__ nrm, long 
 
 using namespace efm;
 
+static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, long B_all, long row_offset, long B_local,
+                            long D, cudaStream_t st) {
+  auto* kpos = reinterpret_cast<unsigned long long*>(ws + L.kpos);
+  auto* kneg = reinterpret_cast<unsigned long long*>(ws + L.kneg);
+  float* sq = reinterpret_cast<float*>(ws + L.sq);
+  int32_t* lab = reinterpret_cast<int32_t*>(ws + L.lab);
+  auto* xm_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + L.xm);
+  float* xm_f32 = reinterpret_cast<float*>(ws + L.xm);
+  if (L.use_tc) {
+    tc::GramParams g{};
+    g.M = (int)B_local; g.N = (int)B_all; g.nk = L.Dp / tc::BK;
+    const int grid = tc::plan_gram(g, 0);
+    MineEpi::Params ep{sq, lab, kpos, kneg, (int)row_offset};
+    int rc = tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, g, ep, grid, st);
+    return rc;
+  } else {
+    const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
+    const int row_blocks = (int)cdiv(B_local, FM);
+    int splits = (int)cdiv(4L * num_sms(), row_blocks);
+    const int CT = (int)cdiv(B_all, FN);
+    if (splits > CT) splits = CT;
+    if (splits < 1) splits = 1;
+    bh_mine_f32_kernel<<<dim3(splits, row_blocks), 256, 0, st>>>(X, sq, lab, (int)B_all, (int)row_offset, (int)B_local,
+                                                                  (int)D, kpos, kneg);
+    EFM_LAUNCH_CHECK("bh_mine_f32");
+  }
+
+  return EFM_OK;
+}
+
 extern "C" size_t efm_bh_workspace_bytes(long B_local, long B_all, long D, int dtype, int flags) {
   if (B_local < 0 || B_all <= 0 || D <= 0) return 0;
   return bh_layout(B_local, B_all, D, dtype, flags).total;
@@ -365,23 +395,9 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   });
   EFM_LAUNCH_CHECK("bh_prep");
 
-  if (L.use_tc) {
-    tc::GramParams g{};
-    g.M = (int)B_local; g.N = (int)B_all; g.nk = L.Dp / tc::BK;
-    const int grid = tc::plan_gram(g, 0);
-    MineEpi::Params ep{sq, lab, kpos, kneg, (int)row_offset};
-    int rc = tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, g, ep, grid, st);
+  {
+    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, st);
     if (rc) return rc;
-  } else {
-    const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
-    const int row_blocks = (int)cdiv(B_local, FM);
-    int splits = (int)cdiv(4L * num_sms(), row_blocks);
-    const int CT = (int)cdiv(B_all, FN);
-    if (splits > CT) splits = CT;
-    if (splits < 1) splits = 1;
-    bh_mine_f32_kernel<<<dim3(splits, row_blocks), 256, 0, st>>>(X, sq, lab, (int)B_all, (int)row_offset, (int)B_local,
-                                                                  (int)D, kpos, kneg);
-    EFM_LAUNCH_CHECK("bh_mine_f32");
   }
 
   EFM_DISPATCH_DTYPE(dtype, T, {
@@ -441,4 +457,17 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
     EFM_LAUNCH_CHECK("bh_norm_bwd");
   }
   return EFM_OK;
+}
+
+// Mining step alone on a workspace prepared by a previous efm_bh_triplet_fwd_bwd call with the same shapes
+// (keys are monotone, so re-mining is idempotent).  For profiling / roofline measurement of the dominant kernel.
+extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long B_local, long D, int dtype, int flags,
+                           void* workspace, size_t ws_bytes, void* stream) {
+  EFM_REQUIRE(B_all > 0 && B_local > 0 && D > 0 && row_offset >= 0 && row_offset + B_local <= B_all, EFM_E_ARG,
+              "efm_bh_mine: bad shape");
+  EFM_REQUIRE(E_all && workspace && aligned(workspace, 256), EFM_E_ARG, "efm_bh_mine: bad pointer");
+  const BhLayout L = bh_layout(B_local, B_all, D, dtype, flags);
+  EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_mine: workspace too small");
+  return bh_launch_mining(L, E_all, static_cast<uint8_t*>(workspace), B_all, row_offset, B_local, D,
+                          static_cast<cudaStream_t>(stream));
 }

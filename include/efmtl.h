@@ -117,6 +117,11 @@ int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_all, long B_
                            int flags, float* loss, int32_t* idx_p, int32_t* idx_n, float* dE_all,
                            void* workspace, size_t ws_bytes, void* stream);
 
+/* The mining kernel alone, on a workspace already prepared by efm_bh_triplet_fwd_bwd with the same shapes
+ * (re-mining is idempotent).  Exists so the dominant kernel can be timed / profiled in isolation. */
+int efm_bh_mine(const void* E_all, long B_all, long row_offset, long B_local, long D, int dtype, int flags,
+                void* workspace, size_t ws_bytes, void* stream);
+
 /* Backward only, for given mined indices and a per-anchor head gradient (autograd over the un-reduced
  * loss vector): dE_all = d(sum_i head_grad_i * loss_i)/dE_all.  dE_all is overwritten. */
 size_t efm_bh_backward_workspace_bytes(long B_all);

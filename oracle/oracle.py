@@ -183,7 +183,7 @@ def batch_hard_triplet(E, labels, margin, normalize=True, E_all=None, labels_all
         dE_all = (dX_all - X_all * (X_all * dX_all).sum(axis=1, keepdims=True)) / nrm_all
     else:
         dE_all = dX_all
-    return dict(loss=loss, idx_p=idx_p, idx_n=idx_n, dE_all=dE_all, X_all=X_all)
+    return dict(loss=loss, idx_p=idx_p, idx_n=idx_n, dE_all=dE_all, X_all=X_all, s=np.where(valid, s, -np.inf))
 
 
 def batch_hard_triplet_fast(E, labels, margin, normalize=True):
