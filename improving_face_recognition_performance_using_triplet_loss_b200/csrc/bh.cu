@@ -22,7 +22,8 @@ struct BhLayout {
   bool use_tc;
   bool xm_f32;          // fp32 mining rows materialised in the workspace
   int Dp;               // K padded to a multiple of 64 (tensor-core path)
-  size_t kpos, kneg, sq, nrm, lab, xm, total;
+  int tbits;            // log2 of the label hash-table size
+  size_t kpos, kneg, sq, nrm, lab, xm, hkeys, hhead, hnext, hslot, total;
 };
 
 BhLayout bh_layout(long B_local, long B_all, long D, int dtype, int flags) {
@@ -30,148 +31,241 @@ BhLayout bh_layout(long B_local, long B_all, long D, int dtype, int flags) {
   L.Dp = (int)(cdiv(D, tc::BK) * tc::BK);
   L.use_tc = (dtype != EFM_F32 || (flags & EFM_BH_MINE_BF16)) && L.Dp <= tc::MAX_NK * tc::BK;
   L.xm_f32 = !L.use_tc && (dtype != EFM_F32 || (flags & EFM_BH_NORMALIZE));
+  L.tbits = 4;
+  while ((1L << L.tbits) < 2 * B_all) ++L.tbits;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.kpos = take((size_t)B_local * 8);
   L.kneg = take((size_t)B_local * 8);
   L.sq = take((size_t)B_all * 4);
   L.nrm = take((size_t)B_all * 4);
-  L.lab = take((size_t)B_all * 4 + 1024);          // +slack: the epilogue reads labels/sq in 128-bit vectors
+  L.lab = take((size_t)B_all * 4);
   L.xm = take(L.use_tc ? (size_t)B_all * L.Dp * 2 : (L.xm_f32 ? (size_t)B_all * D * 4 : 0));
+  // per-label chains (tensor-core path): open-addressing table of (label -> head row), next pointers, slot per row
+  L.hkeys = take(L.use_tc ? (size_t)8 << L.tbits : 0);
+  L.hhead = take(L.use_tc ? (size_t)4 << L.tbits : 0);      // contiguous with hkeys: one memset(0xFF) resets both
+  L.hnext = take(L.use_tc ? (size_t)B_all * 4 : 0);
+  L.hslot = take(L.use_tc ? (size_t)B_all * 4 : 0);
   L.total = off;
   return L;
 }
 
+// 8 consecutive elements -> fp32 (128-bit loads for 16-bit types, 2 x 128-bit for fp32)
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&o)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    union { uint4 raw; T v[8]; } u;
+    u.raw = __ldg(reinterpret_cast<const uint4*>(p));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = El<T>::to_f(u.v[k]);
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ prep
-template <typename T>
+// One warp per row of E_all.  VEC8: D % 8 == 0 and 16-byte aligned rows -> each lane owns 8-element slabs.
+template <typename T, bool VEC8>
 __global__ void __launch_bounds__(WARPS * 32)
 bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long B_all, int D, int Dp, int normalize,
                int use_tc, int write_f32, long row_offset, long B_local, float* __restrict__ sq,
                float* __restrict__ nrm, int32_t* __restrict__ lab_ws, __nv_bfloat16* __restrict__ xm_bf16,
                float* __restrict__ xm_f32, unsigned long long* __restrict__ kpos,
-               unsigned long long* __restrict__ kneg, float* __restrict__ dE) {
+               unsigned long long* __restrict__ kneg, float* __restrict__ dE,
+               unsigned long long* __restrict__ hkeys, int32_t* __restrict__ hhead, int32_t* __restrict__ hnext,
+               int32_t* __restrict__ hslot, int tbits) {
   const long row = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= B_all) return;
   const int lane = threadIdx.x & 31;
   const T* er = E + row * D;
-  float n = 1.f;
-  if (normalize) {
-    float ss = 0.f;
-    for (int d = lane; d < D; d += 32) { const float v = El<T>::to_f(er[d]); ss = fmaf(v, v, ss); }
-    n = sqrtf(warp_sum(ss));
-  }
-  float s2 = 0.f;
-  if (use_tc) {
-    __nv_bfloat16* xr = xm_bf16 + row * Dp;
-    for (int d = lane; d < Dp; d += 32) {
-      float v = 0.f;
-      if (d < D) { v = El<T>::to_f(er[d]); if (normalize) v = v / n; }
-      const __nv_bfloat16 b = __float2bfloat16_rn(v);
-      xr[d] = b;
-      const float vb = __bfloat162float(b);
-      s2 = fmaf(vb, vb, s2);
+  float n = 1.f, s2 = 0.f;
+  if constexpr (VEC8) {
+    if (D <= 256) {                                  // whole row lives in registers: one pass
+      float v[8];
+      const bool act = lane * 8 < D;
+      if (act) load8<T>(er + lane * 8, v);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+      }
+      if (normalize) {
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ss = fmaf(v[k], v[k], ss);
+        n = sqrtf(warp_sum(ss));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = v[k] / n;
+      }
+      if (use_tc) {
+        union { uint4 raw; __nv_bfloat16 b[8]; } u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { u.b[k] = __float2bfloat16_rn(v[k]); const float vb = __bfloat162float(u.b[k]); s2 = fmaf(vb, vb, s2); }
+        if (lane * 8 < Dp) *reinterpret_cast<uint4*>(xm_bf16 + row * Dp + lane * 8) = u.raw;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s2 = fmaf(v[k], v[k], s2);
+        if (write_f32 && act) {
+          float4* o = reinterpret_cast<float4*>(xm_f32 + row * D + lane * 8);
+          o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    } else {
+      if (normalize) {
+        float ss = 0.f;
+        for (int d = lane * 8; d < D; d += 256) { float v[8]; load8<T>(er + d, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) ss = fmaf(v[k], v[k], ss); }
+        n = sqrtf(warp_sum(ss));
+      }
+      for (int d = lane * 8; d < Dp; d += 256) {
+        float v[8];
+        if (d < D) load8<T>(er + d, v);
+        else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = 0.f;
+        }
+        if (normalize) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = v[k] / n;
+        }
+        if (use_tc) {
+          union { uint4 raw; __nv_bfloat16 b[8]; } u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { u.b[k] = __float2bfloat16_rn(v[k]); const float vb = __bfloat162float(u.b[k]); s2 = fmaf(vb, vb, s2); }
+          *reinterpret_cast<uint4*>(xm_bf16 + row * Dp + d) = u.raw;
+        } else if (d < D) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s2 = fmaf(v[k], v[k], s2);
+          if (write_f32) {
+            float4* o = reinterpret_cast<float4*>(xm_f32 + row * D + d);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+      }
+    }
+    if (dE) {
+      float4* z = reinterpret_cast<float4*>(dE + row * D);
+      for (int d4 = lane; d4 < D / 4; d4 += 32) z[d4] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else {
-    for (int d = lane; d < D; d += 32) {
-      float v = El<T>::to_f(er[d]);
-      if (normalize) v = v / n;
-      if (write_f32) xm_f32[row * D + d] = v;
-      s2 = fmaf(v, v, s2);
+    if (normalize) {
+      float ss = 0.f;
+      for (int d = lane; d < D; d += 32) { const float v = El<T>::to_f(er[d]); ss = fmaf(v, v, ss); }
+      n = sqrtf(warp_sum(ss));
     }
+    if (use_tc) {
+      __nv_bfloat16* xr = xm_bf16 + row * Dp;
+      for (int d = lane; d < Dp; d += 32) {
+        float v = 0.f;
+        if (d < D) { v = El<T>::to_f(er[d]); if (normalize) v = v / n; }
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        xr[d] = b;
+        const float vb = __bfloat162float(b);
+        s2 = fmaf(vb, vb, s2);
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        float v = El<T>::to_f(er[d]);
+        if (normalize) v = v / n;
+        if (write_f32) xm_f32[row * D + d] = v;
+        s2 = fmaf(v, v, s2);
+      }
+    }
+    if (dE) for (int d = lane; d < D; d += 32) dE[row * D + d] = 0.f;
   }
   s2 = warp_sum(s2);
-  if (dE) for (int d = lane; d < D; d += 32) dE[row * D + d] = 0.f;
   if (lane == 0) {
     sq[row] = s2;
     nrm[row] = n;
-    if (lab_ws) lab_ws[row] = labels[row];
+    const int32_t lab = labels ? labels[row] : 0;
+    if (lab_ws) lab_ws[row] = lab;
     const long li = row - row_offset;
     if (kpos && li >= 0 && li < B_local) { kpos[li] = KEY_POS_EMPTY; kneg[li] = KEY_NEG_EMPTY; }
+    if (hkeys) {                                     // push this row on its label's chain
+      const unsigned long long tag = (unsigned long long)(uint32_t)lab;     // upper half 0: never equals EMPTY (~0)
+      const uint32_t mask = (1u << tbits) - 1u;
+      uint32_t sl = ((uint32_t)lab * 2654435761u) >> (32 - tbits);
+      for (;;) {
+        const unsigned long long old = atomicCAS(&hkeys[sl], ~0ull, tag);
+        if (old == ~0ull || old == tag) break;
+        sl = (sl + 1) & mask;
+      }
+      hslot[row] = (int32_t)sl;
+      hnext[row] = atomicExch(&hhead[sl], (int32_t)row);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------ mining epilogue (tcgen05 path)
+// Hardest NEGATIVE only, branch-free per element: v_ij = same_label ? +inf : |x_j|^2 - 2 g_ij (same order as
+// d_ij for a fixed anchor; the anchor itself is a same-label column).  Per 32-column chunk: 8 group-of-4 minima,
+// their minimum, and -- only when that beats the running best -- the index of the winning GROUP.  The column
+// inside the group is resolved by bh_finalize with exact fp32 distances (4 candidates per anchor), so the hot
+// loop carries no per-element index bookkeeping.  Hardest POSITIVES are mined in bh_finalize from the per-label
+// chains (a handful of candidates per anchor).
 struct MineEpi {
   static constexpr int SMEM_PER_WARP = 0;
   struct Params {
-    const float* sq;          // |x_j|^2 of the mining rows, (B_all + pad)
-    const int32_t* labels;    // (B_all + pad)
-    unsigned long long* kpos; // (B_local)
-    unsigned long long* kneg;
+    const float* sq;          // |x_j|^2 of the mining rows, (B_all)
+    const int32_t* labels;    // (B_all)
+    unsigned long long* kneg; // (B_local): (ord(v) << 32) | first column of the winning group of 4
     int row_offset;
   };
   struct State {
-    int lab_i, gi;
-    float pbest, nbest;
-    int pidx, nidx;
+    int lab_i;
+    float nbest;
+    int ngrp;
     bool valid;
   };
   static __device__ __forceinline__ void row_begin(const Params& p, const tc::GramParams& g, int row, State& s) {
     s.valid = row < g.M;
-    s.gi = p.row_offset + row;
-    s.lab_i = s.valid ? p.labels[s.gi] : 0;
-    s.pbest = -INFINITY; s.nbest = INFINITY;
-    s.pidx = -1; s.nidx = -1;
-  }
-  // exact per-element tracking (used when the chunk holds a same-label column, or at the ragged edge)
-  static __device__ __forceinline__ void slow(State& s, const float (&v)[32], const int (&lab)[32], int col0, int ncols) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      if (k < ncols) {
-        const int col = col0 + k;
-        if (lab[k] == s.lab_i) {
-          if (col != s.gi && v[k] > s.pbest) { s.pbest = v[k]; s.pidx = col; }
-        } else if (v[k] < s.nbest) { s.nbest = v[k]; s.nidx = col; }
-      }
-    }
+    s.lab_i = s.valid ? p.labels[p.row_offset + row] : 0;
+    s.nbest = INFINITY;
+    s.ngrp = -1;
   }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
                                                const uint32_t (&acc)[32], int col0, float*) {
     const int ncols = g.N - col0;                    // > 0 guaranteed by the caller
-    float v[32];
-    int lab[32];
+    float pm[8];                                     // group-of-4 minima
     if (ncols >= 32) {
       const float4* sq4 = reinterpret_cast<const float4*>(p.sq + col0);
       const int4* lb4 = reinterpret_cast<const int4*>(p.labels + col0);
-      bool any_same = false;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 s4 = __ldg(sq4 + q);
         const int4 l4 = __ldg(lb4 + q);
-        v[4 * q + 0] = fmaf(-2.f, __uint_as_float(acc[4 * q + 0]), s4.x);
-        v[4 * q + 1] = fmaf(-2.f, __uint_as_float(acc[4 * q + 1]), s4.y);
-        v[4 * q + 2] = fmaf(-2.f, __uint_as_float(acc[4 * q + 2]), s4.z);
-        v[4 * q + 3] = fmaf(-2.f, __uint_as_float(acc[4 * q + 3]), s4.w);
-        lab[4 * q + 0] = l4.x; lab[4 * q + 1] = l4.y; lab[4 * q + 2] = l4.z; lab[4 * q + 3] = l4.w;
-        any_same |= (l4.x == s.lab_i) | (l4.y == s.lab_i) | (l4.z == s.lab_i) | (l4.w == s.lab_i);
-      }
-      if (any_same) {
-        slow(s, v, lab, col0, 32);
-      } else {
-        float m = v[0];
-#pragma unroll
-        for (int k = 1; k < 32; ++k) m = fminf(m, v[k]);
-        if (m < s.nbest) {
-          int kk = 31;
-#pragma unroll
-          for (int k = 30; k >= 0; --k) kk = (v[k] == m) ? k : kk;
-          s.nbest = m; s.nidx = col0 + kk;
-        }
+        const float v0 = fmaf(-2.f, __uint_as_float(acc[4 * q + 0]), (l4.x == s.lab_i) ? INFINITY : s4.x);
+        const float v1 = fmaf(-2.f, __uint_as_float(acc[4 * q + 1]), (l4.y == s.lab_i) ? INFINITY : s4.y);
+        const float v2 = fmaf(-2.f, __uint_as_float(acc[4 * q + 2]), (l4.z == s.lab_i) ? INFINITY : s4.z);
+        const float v3 = fmaf(-2.f, __uint_as_float(acc[4 * q + 3]), (l4.w == s.lab_i) ? INFINITY : s4.w);
+        pm[q] = fminf(fminf(fminf(v0, v1), v2), v3);                   // FMNMX3 + FMNMX
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const bool in = k < ncols;
-        v[k] = in ? fmaf(-2.f, __uint_as_float(acc[k]), p.sq[col0 + k]) : 0.f;
-        lab[k] = in ? p.labels[col0 + k] : 0;
+      for (int q = 0; q < 8; ++q) {
+        float m4 = INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 4 * q + e;
+          if (k < ncols) {
+            const float sqv = (p.labels[col0 + k] == s.lab_i) ? INFINITY : p.sq[col0 + k];
+            m4 = fminf(m4, fmaf(-2.f, __uint_as_float(acc[k]), sqv));
+          }
+        }
+        pm[q] = m4;
       }
-      slow(s, v, lab, col0, ncols);
+    }
+    const float m = fminf(fminf(fminf(fminf(pm[0], pm[1]), pm[2]), fminf(fminf(pm[3], pm[4]), pm[5])), fminf(pm[6], pm[7]));
+    if (m < s.nbest) {                               // strict: the earlier group survives ties
+      int q = 7;
+#pragma unroll
+      for (int t = 6; t >= 0; --t) q = (pm[t] == m) ? t : q;
+      s.nbest = m;
+      s.ngrp = col0 + 4 * q;
     }
   }
   static __device__ __forceinline__ void row_end(const Params& p, const tc::GramParams&, int row, int, State& s) {
-    if (!s.valid) return;
-    if (s.pidx >= 0) atomicMax(&p.kpos[row], key_pos(s.pbest, s.pidx));
-    if (s.nidx >= 0) atomicMin(&p.kneg[row], key_neg(s.nbest, s.nidx));
+    if (s.valid && s.ngrp >= 0) atomicMin(&p.kneg[row], key_neg(s.nbest, s.ngrp));
   }
 };
 
@@ -259,35 +353,86 @@ bh_mine_f32_kernel(const float* __restrict__ X, const float* __restrict__ sq, co
 }
 
 // ------------------------------------------------------------------------------------------ finalize
-template <typename T>
+// squared distance between two bf16 mining rows, warp-cooperative, fp32 direct differences
+__device__ __forceinline__ float xm_dist(const __nv_bfloat16* a, const __nv_bfloat16* b, int Dp, int lane) {
+  float s = 0.f;
+  for (int d = lane * 8; d < Dp; d += 256) {
+    float x[8], y[8];
+    load8<__nv_bfloat16>(a + d, x);
+    load8<__nv_bfloat16>(b + d, y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float t = x[k] - y[k]; s = fmaf(t, t, s); }
+  }
+  return warp_sum(s);
+}
+
+// One warp per anchor.  mode 0: kpos/kneg hold exact indices (fp32 mining kernel).  mode 1 (tensor-core path):
+// hardest positive from the anchor's label chain, hardest negative = best non-same-label column inside the
+// group of 4 the Gram kernel selected; both by exact fp32 distances on the bf16 mining rows.  mode 2: indices given.
+template <typename T, bool VEC8>
 __global__ void __launch_bounds__(WARPS * 32)
 bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int normalize, long B_all, int D,
                    long row_offset, long B_local, float margin, const float* __restrict__ head_grad, int detach,
-                   const unsigned long long* __restrict__ kpos, const unsigned long long* __restrict__ kneg,
-                   float* __restrict__ loss, int32_t* __restrict__ idx_p, int32_t* __restrict__ idx_n,
-                   float* __restrict__ dE) {
+                   int mode, const unsigned long long* __restrict__ kpos, const unsigned long long* __restrict__ kneg,
+                   const __nv_bfloat16* __restrict__ xm, int Dp, const int32_t* __restrict__ lab,
+                   const int32_t* __restrict__ hhead, const int32_t* __restrict__ hnext,
+                   const int32_t* __restrict__ hslot, float* __restrict__ loss, int32_t* __restrict__ idx_p,
+                   int32_t* __restrict__ idx_n, float* __restrict__ dE) {
   const long li = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (li >= B_local) return;
   const int lane = threadIdx.x & 31;
-  int ip, in;
-  if (kpos) {                                               // decode the mined keys
+  const long gi = row_offset + li;
+  int ip = -1, in = -1;
+  if (mode == 0) {
     const unsigned long long kp = kpos[li], kn = kneg[li];
     ip = (kp == KEY_POS_EMPTY) ? -1 : (int)(0xffffffffu - (uint32_t)(kp & 0xffffffffull));
     in = (kn == KEY_NEG_EMPTY) ? -1 : (int)(uint32_t)(kn & 0xffffffffull);
-    if (lane == 0) { idx_p[li] = ip; idx_n[li] = in; }
-  } else {                                                  // backward-only call: indices given
+  } else if (mode == 1) {
+    const __nv_bfloat16* xi = xm + gi * Dp;
+    float bd = -INFINITY;
+    for (int j = hhead[hslot[gi]]; j >= 0; j = hnext[j]) {          // same-label rows (chain order is arbitrary)
+      if (j == gi) continue;
+      const float d = xm_dist(xi, xm + (long)j * Dp, Dp, lane);
+      if (d > bd || (d == bd && j < ip) || ip < 0) { bd = d; ip = j; }
+    }
+    const unsigned long long kn = kneg[li];
+    if (kn != KEY_NEG_EMPTY) {
+      const int g0 = (int)(uint32_t)(kn & 0xffffffffull);
+      const int my = lab[gi];
+      float nd = INFINITY;
+      for (int c = g0; c < g0 + 4 && c < B_all; ++c) {               // ascending + strict '<': lowest index on ties
+        if (lab[c] == my) continue;
+        const float d = xm_dist(xi, xm + (long)c * Dp, Dp, lane);
+        if (d < nd || in < 0) { nd = d; in = c; }
+      }
+    }
+  } else {
     ip = idx_p[li]; in = idx_n[li];
   }
+  if (mode != 2 && lane == 0) { idx_p[li] = ip; idx_n[li] = in; }
   if (ip < 0 || in < 0 || ip >= B_all || in >= B_all) { if (lane == 0 && loss) loss[li] = 0.f; return; }
-  const long gi = row_offset + li;
   const T* ea = E + gi * D; const T* epp = E + (long)ip * D; const T* en = E + (long)in * D;
   const float na = normalize ? nrm[gi] : 1.f, np_ = normalize ? nrm[ip] : 1.f, nn = normalize ? nrm[in] : 1.f;
   float s = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float a = El<T>::to_f(ea[d]), p = El<T>::to_f(epp[d]), n = El<T>::to_f(en[d]);
-    if (normalize) { a = a / na; p = p / np_; n = n / nn; }
-    const float dp = p - a, dn = n - a;
-    s += dp * dp - dn * dn;
+  if constexpr (VEC8) {
+    for (int d = lane * 8; d < D; d += 256) {
+      float a[8], p[8], n[8];
+      load8<T>(ea + d, a); load8<T>(epp + d, p); load8<T>(en + d, n);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float av = a[k], pv = p[k], nv = n[k];
+        if (normalize) { av = av / na; pv = pv / np_; nv = nv / nn; }
+        const float dp = pv - av, dn = nv - av;
+        s += dp * dp - dn * dn;
+      }
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      float a = El<T>::to_f(ea[d]), p = El<T>::to_f(epp[d]), n = El<T>::to_f(en[d]);
+      if (normalize) { a = a / na; p = p / np_; n = n / nn; }
+      const float dp = p - a, dn = n - a;
+      s += dp * dp - dn * dn;
+    }
   }
   s = warp_sum(s);
   const float l = fmaxf(s + margin, 0.f);
@@ -297,16 +442,40 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
   if (w2 == 0.f) return;
   const bool p_ok = !detach || (ip >= row_offset && ip < row_offset + B_local);
   const bool n_ok = !detach || (in >= row_offset && in < row_offset + B_local);
-  for (int d = lane; d < D; d += 32) {
-    float a = El<T>::to_f(ea[d]), p = El<T>::to_f(epp[d]), n = El<T>::to_f(en[d]);
-    if (normalize) { a = a / na; p = p / np_; n = n / nn; }
-    atomicAdd(&dE[gi * D + d], w2 * (n - p));
-    if (p_ok) atomicAdd(&dE[(long)ip * D + d], w2 * (p - a));
-    if (n_ok) atomicAdd(&dE[(long)in * D + d], w2 * (a - n));
+  if constexpr (VEC8) {
+    for (int d = lane * 8; d < D; d += 256) {
+      float a[8], p[8], n[8];
+      load8<T>(ea + d, a); load8<T>(epp + d, p); load8<T>(en + d, n);
+      if (normalize) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a[k] = a[k] / na; p[k] = p[k] / np_; n[k] = n[k] / nn; }
+      }
+      float4* ga = reinterpret_cast<float4*>(dE + gi * D + d);
+      atomicAdd(ga, make_float4(w2 * (n[0] - p[0]), w2 * (n[1] - p[1]), w2 * (n[2] - p[2]), w2 * (n[3] - p[3])));
+      atomicAdd(ga + 1, make_float4(w2 * (n[4] - p[4]), w2 * (n[5] - p[5]), w2 * (n[6] - p[6]), w2 * (n[7] - p[7])));
+      if (p_ok) {
+        float4* gp = reinterpret_cast<float4*>(dE + (long)ip * D + d);
+        atomicAdd(gp, make_float4(w2 * (p[0] - a[0]), w2 * (p[1] - a[1]), w2 * (p[2] - a[2]), w2 * (p[3] - a[3])));
+        atomicAdd(gp + 1, make_float4(w2 * (p[4] - a[4]), w2 * (p[5] - a[5]), w2 * (p[6] - a[6]), w2 * (p[7] - a[7])));
+      }
+      if (n_ok) {
+        float4* gn = reinterpret_cast<float4*>(dE + (long)in * D + d);
+        atomicAdd(gn, make_float4(w2 * (a[0] - n[0]), w2 * (a[1] - n[1]), w2 * (a[2] - n[2]), w2 * (a[3] - n[3])));
+        atomicAdd(gn + 1, make_float4(w2 * (a[4] - n[4]), w2 * (a[5] - n[5]), w2 * (a[6] - n[6]), w2 * (a[7] - n[7])));
+      }
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      float a = El<T>::to_f(ea[d]), p = El<T>::to_f(epp[d]), n = El<T>::to_f(en[d]);
+      if (normalize) { a = a / na; p = p / np_; n = n / nn; }
+      atomicAdd(&dE[gi * D + d], w2 * (n - p));
+      if (p_ok) atomicAdd(&dE[(long)ip * D + d], w2 * (p - a));
+      if (n_ok) atomicAdd(&dE[(long)in * D + d], w2 * (a - n));
+    }
   }
 }
 
-template <typename T>
+template <typename T, bool VEC8>
 __global__ void __launch_bounds__(WARPS * 32)
 bh_norm_bwd_kernel(const T* __restrict__ E, const float* __restrict__ nrm, long B_all, int D, float* __restrict__ dE) {
   const long row = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -314,6 +483,26 @@ bh_norm_bwd_kernel(const T* __restrict__ E, const float* __restrict__ nrm, long 
   const int lane = threadIdx.x & 31;
   const float n = nrm[row];
   float dot = 0.f;
+  if constexpr (VEC8) {
+    if (D <= 256) {                                  // one pass, row in registers
+      float x[8], gq[8];
+      const bool act = lane * 8 < D;
+      float4* gp = reinterpret_cast<float4*>(dE + row * D + lane * 8);
+      if (act) {
+        load8<T>(E + row * D + lane * 8, x);
+        const float4 g0 = gp[0], g1 = gp[1];
+        gq[0] = g0.x; gq[1] = g0.y; gq[2] = g0.z; gq[3] = g0.w; gq[4] = g1.x; gq[5] = g1.y; gq[6] = g1.z; gq[7] = g1.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x[k] = x[k] / n; dot = fmaf(x[k], gq[k], dot); }
+      }
+      dot = warp_sum(dot);
+      if (act) {
+        gp[0] = make_float4((gq[0] - x[0] * dot) / n, (gq[1] - x[1] * dot) / n, (gq[2] - x[2] * dot) / n, (gq[3] - x[3] * dot) / n);
+        gp[1] = make_float4((gq[4] - x[4] * dot) / n, (gq[5] - x[5] * dot) / n, (gq[6] - x[6] * dot) / n, (gq[7] - x[7] * dot) / n);
+      }
+      return;
+    }
+  }
   for (int d = lane; d < D; d += 32) dot = fmaf(El<T>::to_f(E[row * D + d]) / n, dE[row * D + d], dot);
   dot = warp_sum(dot);
   for (int d = lane; d < D; d += 32) {
@@ -339,23 +528,29 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
     tc::GramParams g{};
     g.M = (int)B_local; g.N = (int)B_all; g.nk = L.Dp / tc::BK;
     const int grid = tc::plan_gram(g, 0);
-    MineEpi::Params ep{sq, lab, kpos, kneg, (int)row_offset};
-    int rc = tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, g, ep, grid, st);
-    return rc;
-  } else {
-    const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
-    const int row_blocks = (int)cdiv(B_local, FM);
-    int splits = (int)cdiv(4L * num_sms(), row_blocks);
-    const int CT = (int)cdiv(B_all, FN);
-    if (splits > CT) splits = CT;
-    if (splits < 1) splits = 1;
-    bh_mine_f32_kernel<<<dim3(splits, row_blocks), 256, 0, st>>>(X, sq, lab, (int)B_all, (int)row_offset, (int)B_local,
-                                                                  (int)D, kpos, kneg);
-    EFM_LAUNCH_CHECK("bh_mine_f32");
+    MineEpi::Params ep{sq, lab, kneg, (int)row_offset};
+    return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, g, ep, grid, st);
   }
-
+  const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
+  const int row_blocks = (int)cdiv(B_local, FM);
+  int splits = (int)cdiv(4L * num_sms(), row_blocks);
+  const int CT = (int)cdiv(B_all, FN);
+  if (splits > CT) splits = CT;
+  if (splits < 1) splits = 1;
+  bh_mine_f32_kernel<<<dim3(splits, row_blocks), 256, 0, st>>>(X, sq, lab, (int)B_all, (int)row_offset, (int)B_local,
+                                                                (int)D, kpos, kneg);
+  EFM_LAUNCH_CHECK("bh_mine_f32");
   return EFM_OK;
 }
+
+static bool bh_vec8(const void* E, long D, const float* dE) {
+  return (D % 8 == 0) && aligned(E, 16) && (!dE || aligned(dE, 16));
+}
+
+#define EFM_BH_DISPATCH(dtype, vec, T, V, ...)                                              \
+  EFM_DISPATCH_DTYPE(dtype, T, {                                                            \
+    if (vec) { constexpr bool V = true; __VA_ARGS__; } else { constexpr bool V = false; __VA_ARGS__; } \
+  })
 
 extern "C" size_t efm_bh_workspace_bytes(long B_local, long B_all, long D, int dtype, int flags) {
   if (B_local < 0 || B_all <= 0 || D <= 0) return 0;
@@ -368,7 +563,7 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
                                       size_t ws_bytes, void* stream) {
   EFM_REQUIRE(B_all > 0 && B_local >= 0 && D > 0 && row_offset >= 0 && row_offset + B_local <= B_all, EFM_E_ARG,
               "efm_bh_triplet_fwd_bwd: bad shape B_all=%ld row_offset=%ld B_local=%ld D=%ld", B_all, row_offset, B_local, D);
-  EFM_REQUIRE(B_all < (1L << 31) - 512 && D < (1 << 20), EFM_E_ARG, "efm_bh_triplet_fwd_bwd: shape too large");
+  EFM_REQUIRE(B_all < (1L << 30) && D < (1 << 20), EFM_E_ARG, "efm_bh_triplet_fwd_bwd: shape too large");
   EFM_REQUIRE(E_all && labels_all && loss && idx_p && idx_n && workspace, EFM_E_ARG, "efm_bh_triplet_fwd_bwd: null pointer");
   EFM_REQUIRE(dtype == EFM_F32 || dtype == EFM_BF16 || dtype == EFM_F16, EFM_E_ARG, "efm_bh_triplet_fwd_bwd: dtype %d", dtype);
   EFM_REQUIRE(aligned(workspace, 256), EFM_E_ALIGN, "efm_bh_triplet_fwd_bwd: workspace must be 256-byte aligned");
@@ -384,31 +579,38 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   int32_t* lab = reinterpret_cast<int32_t*>(ws + L.lab);
   auto* xm_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + L.xm);
   float* xm_f32 = reinterpret_cast<float*>(ws + L.xm);
+  auto* hkeys = L.use_tc ? reinterpret_cast<unsigned long long*>(ws + L.hkeys) : nullptr;
+  int32_t* hhead = reinterpret_cast<int32_t*>(ws + L.hhead);
+  int32_t* hnext = reinterpret_cast<int32_t*>(ws + L.hnext);
+  int32_t* hslot = reinterpret_cast<int32_t*>(ws + L.hslot);
   const int normalize = (flags & EFM_BH_NORMALIZE) ? 1 : 0;
   const int detach = (flags & EFM_BH_DETACH_GATHERED) ? 1 : 0;
   const unsigned grid_all = (unsigned)cdiv(B_all, WARPS), grid_loc = (unsigned)cdiv(B_local, WARPS);
+  const bool vec = bh_vec8(E_all, D, dE_all);
 
-  EFM_DISPATCH_DTYPE(dtype, T, {
-    bh_prep_kernel<T><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, labels_all, B_all, (int)D, L.Dp, normalize,
-                                                       L.use_tc ? 1 : 0, L.xm_f32 ? 1 : 0, row_offset, B_local, sq, nrm,
-                                                       lab, xm_bf16, xm_f32, kpos, kneg, dE_all);
+  if (L.use_tc)                                                   // empty label table: keys = ~0, heads = -1
+    EFM_CUDA(cudaMemsetAsync(ws + L.hkeys, 0xFF, (L.hhead - L.hkeys) + ((size_t)4 << L.tbits), st));
+  EFM_BH_DISPATCH(dtype, vec, T, V, {
+    bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, labels_all, B_all, (int)D, L.Dp, normalize,
+                                                          L.use_tc ? 1 : 0, L.xm_f32 ? 1 : 0, row_offset, B_local, sq, nrm,
+                                                          lab, xm_bf16, xm_f32, kpos, kneg, dE_all, hkeys, hhead, hnext,
+                                                          hslot, L.tbits);
   });
   EFM_LAUNCH_CHECK("bh_prep");
-
   {
     int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, st);
     if (rc) return rc;
   }
-
-  EFM_DISPATCH_DTYPE(dtype, T, {
-    bh_finalize_kernel<T><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                           B_local, margin, head_grad, detach, kpos, kneg, loss, idx_p,
-                                                           idx_n, dE_all);
+  EFM_BH_DISPATCH(dtype, vec, T, V, {
+    bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
+                                                              B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos,
+                                                              kneg, xm_bf16, L.Dp, lab, hhead, hnext, hslot, loss, idx_p,
+                                                              idx_n, dE_all);
   });
   EFM_LAUNCH_CHECK("bh_finalize");
   if (dE_all && normalize) {
-    EFM_DISPATCH_DTYPE(dtype, T, {
-      bh_norm_bwd_kernel<T><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, B_all, (int)D, dE_all);
+    EFM_BH_DISPATCH(dtype, vec, T, V, {
+      bh_norm_bwd_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, B_all, (int)D, dE_all);
     });
     EFM_LAUNCH_CHECK("bh_norm_bwd");
   }
@@ -416,7 +618,7 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
 }
 
 // Backward for given mined indices (head_grad per anchor): used when the loss vector was returned
-// un-reduced and autograd later supplies d(total)/d(loss_i).  workspace: B_all floats (row norms).
+// un-reduced and autograd later supplies d(total)/d(loss_i).  workspace: 2 x B_all floats (row norms, scratch).
 extern "C" size_t efm_bh_backward_workspace_bytes(long B_all) { return align_up((size_t)(B_all > 0 ? B_all : 0) * 4, 256) * 2 + 1024; }
 
 extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, long B_local, long D, int dtype,
@@ -433,26 +635,26 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
   const int normalize = (flags & EFM_BH_NORMALIZE) ? 1 : 0;
   const int detach = (flags & EFM_BH_DETACH_GATHERED) ? 1 : 0;
   const unsigned grid_all = (unsigned)cdiv(B_all, WARPS), grid_loc = (unsigned)cdiv(B_local, WARPS);
-  EFM_CUDA(cudaMemsetAsync(dE_all, 0, (size_t)B_all * D * 4, st));
-  if (normalize) {
-    EFM_DISPATCH_DTYPE(dtype, T, {
-      // reuse the row-norm pass of prep without touching keys / mining rows: a (B_all, D) l2norm stats pass
-      bh_prep_kernel<T><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nullptr, B_all, (int)D, (int)D, 1, 0, 0, 0, 0, sq, nrm,
-                                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-    });
-    EFM_LAUNCH_CHECK("bh_prep(stats)");
-  }
+  const bool vec = bh_vec8(E_all, D, dE_all);
+  // row norms (if normalising) + zeroed dE in one pass: prep with every optional output disabled
+  EFM_BH_DISPATCH(dtype, vec, T, V, {
+    bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nullptr, B_all, (int)D, (int)D, normalize, 0, 0, 0, 0,
+                                                          sq, nrm, nullptr, nullptr, nullptr, nullptr, nullptr, dE_all, nullptr,
+                                                          nullptr, nullptr, nullptr, 0);
+  });
+  EFM_LAUNCH_CHECK("bh_prep(stats)");
   if (B_local > 0) {
-    EFM_DISPATCH_DTYPE(dtype, T, {
-      bh_finalize_kernel<T><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                             B_local, margin, head_grad, detach, nullptr, nullptr, nullptr,
-                                                             const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), dE_all);
+    EFM_BH_DISPATCH(dtype, vec, T, V, {
+      bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
+                                                                B_local, margin, head_grad, detach, 2, nullptr, nullptr, nullptr,
+                                                                0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), dE_all);
     });
     EFM_LAUNCH_CHECK("bh_finalize(bwd)");
   }
   if (normalize) {
-    EFM_DISPATCH_DTYPE(dtype, T, {
-      bh_norm_bwd_kernel<T><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, B_all, (int)D, dE_all);
+    EFM_BH_DISPATCH(dtype, vec, T, V, {
+      bh_norm_bwd_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, B_all, (int)D, dE_all);
     });
     EFM_LAUNCH_CHECK("bh_norm_bwd");
   }

@@ -135,6 +135,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait + make the destination registers data-dependent on the wait, so no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // ---- tile schedule -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_range(const GramParams& g, long& t0, long& t1) {
@@ -274,14 +284,28 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * BN + half * (BN / 2));
-#pragma unroll 1
-      for (int c = 0; c < BN / 2 / 32; ++c) {
-        const int col0 = ct * BN + half * (BN / 2) + c * 32;
-        if (col0 >= g.N) break;                                      // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(t_acc + c * 32, v);
-        tmem_ld_wait();
-        Epi::chunk(ep, g, st, row, v, col0, scratch);
+      const int colh = ct * BN + half * (BN / 2);                    // first column of this warp's half tile
+      // 4 chunks of 32 columns, TMEM loads software-pipelined: chunk c+1 is in flight while chunk c is consumed
+      uint32_t va[32], vb[32];
+      if (colh < g.N) {                                              // warp-uniform
+        tmem_ld32(t_acc, va);
+        tmem_ld_wait(va);
+        if (colh + 32 < g.N) tmem_ld32(t_acc + 32, vb);
+        Epi::chunk(ep, g, st, row, va, colh, scratch);
+        if (colh + 32 < g.N) {
+          tmem_ld_wait(vb);
+          if (colh + 64 < g.N) tmem_ld32(t_acc + 64, va);
+          Epi::chunk(ep, g, st, row, vb, colh + 32, scratch);
+          if (colh + 64 < g.N) {
+            tmem_ld_wait(va);
+            if (colh + 96 < g.N) tmem_ld32(t_acc + 96, vb);
+            Epi::chunk(ep, g, st, row, va, colh + 64, scratch);
+            if (colh + 96 < g.N) {
+              tmem_ld_wait(vb);
+              Epi::chunk(ep, g, st, row, vb, colh + 96, scratch);
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
