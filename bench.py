@@ -291,7 +291,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(B * 12), "ms_per_step": t_e2e * 1e3,
                     "how": "public API batch_hard_triplet(), pinned host E+labels -> device, loss+idx_p+idx_n -> pinned host, "
                            "stream sync every step, wall clock"},
-            "gpu_launches": 4 * args.steps, "launches_per_step": ["bh_prep", "gram_kernel<MineEpi>", "bh_finalize", "bh_norm_bwd"],
+            "gpu_launches": 4 * args.steps, "launches_per_step": ["bh_prep", "gram_kernel<MineEpi>", "bh_finalize", "bh_grad"], "memsets_per_step": 1,
             "clocks": clocks,
             "pairs_per_s": (float(B) * G * world) / (t_step * 1e-3),
         }

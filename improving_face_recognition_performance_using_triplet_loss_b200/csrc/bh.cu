@@ -23,7 +23,7 @@ struct BhLayout {
   bool xm_f32;          // fp32 mining rows materialised in the workspace
   int Dp;               // K padded to a multiple of 64 (tensor-core path)
   int tbits;            // log2 of the label hash-table size
-  size_t kpos, kneg, sq, nrm, lab, xm, hkeys, hhead, hnext, hslot, total;
+  size_t kpos, kneg, sq, nrm, lab, xm, hkeys, hhead, rheadp, rheadn, hnext, hslot, rnextp, rnextn, wgt, clr_begin, clr_bytes, total;
 };
 
 BhLayout bh_layout(long B_local, long B_all, long D, int dtype, int flags) {
@@ -42,10 +42,18 @@ BhLayout bh_layout(long B_local, long B_all, long D, int dtype, int flags) {
   L.lab = take((size_t)B_all * 4);
   L.xm = take(L.use_tc ? (size_t)B_all * L.Dp * 2 : (L.xm_f32 ? (size_t)B_all * D * 4 : 0));
   // per-label chains (tensor-core path): open-addressing table of (label -> head row), next pointers, slot per row
+  // one memset(0xFF) resets [hkeys | hhead | rheadp | rheadn]: empty label table, empty chains (-1 heads)
   L.hkeys = take(L.use_tc ? (size_t)8 << L.tbits : 0);
-  L.hhead = take(L.use_tc ? (size_t)4 << L.tbits : 0);      // contiguous with hkeys: one memset(0xFF) resets both
+  L.hhead = take(L.use_tc ? (size_t)4 << L.tbits : 0);
+  L.rheadp = take((size_t)B_all * 4);                        // rows that chose r as hardest positive (chain heads)
+  L.rheadn = take((size_t)B_all * 4);                        // rows that chose r as hardest negative
+  L.clr_begin = L.use_tc ? L.hkeys : L.rheadp;
+  L.clr_bytes = off - L.clr_begin;
   L.hnext = take(L.use_tc ? (size_t)B_all * 4 : 0);
   L.hslot = take(L.use_tc ? (size_t)B_all * 4 : 0);
+  L.rnextp = take((size_t)B_local * 4);
+  L.rnextn = take((size_t)B_local * 4);
+  L.wgt = take((size_t)B_local * 4);                         // 2 * head_grad_i for active anchors, else 0
   L.total = off;
   return L;
 }
@@ -377,7 +385,8 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
                    const __nv_bfloat16* __restrict__ xm, int Dp, const int32_t* __restrict__ lab,
                    const int32_t* __restrict__ hhead, const int32_t* __restrict__ hnext,
                    const int32_t* __restrict__ hslot, float* __restrict__ loss, int32_t* __restrict__ idx_p,
-                   int32_t* __restrict__ idx_n, float* __restrict__ dE) {
+                   int32_t* __restrict__ idx_n, float* __restrict__ wgt, int32_t* __restrict__ rheadp,
+                   int32_t* __restrict__ rheadn, int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn) {
   const long li = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (li >= B_local) return;
   const int lane = threadIdx.x & 31;
@@ -410,7 +419,10 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     ip = idx_p[li]; in = idx_n[li];
   }
   if (mode != 2 && lane == 0) { idx_p[li] = ip; idx_n[li] = in; }
-  if (ip < 0 || in < 0 || ip >= B_all || in >= B_all) { if (lane == 0 && loss) loss[li] = 0.f; return; }
+  if (ip < 0 || in < 0 || ip >= B_all || in >= B_all) {
+    if (lane == 0) { if (loss) loss[li] = 0.f; if (wgt) wgt[li] = 0.f; }
+    return;
+  }
   const T* ea = E + gi * D; const T* epp = E + (long)ip * D; const T* en = E + (long)in * D;
   const float na = normalize ? nrm[gi] : 1.f, np_ = normalize ? nrm[ip] : 1.f, nn = normalize ? nrm[in] : 1.f;
   float s = 0.f;
@@ -436,78 +448,127 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
   }
   s = warp_sum(s);
   const float l = fmaxf(s + margin, 0.f);
-  if (lane == 0 && loss) loss[li] = l;
-  if (!dE || !(l > 0.f)) return;
-  const float w2 = 2.f * (head_grad ? head_grad[li] : 1.f);
-  if (w2 == 0.f) return;
-  const bool p_ok = !detach || (ip >= row_offset && ip < row_offset + B_local);
-  const bool n_ok = !detach || (in >= row_offset && in < row_offset + B_local);
-  if constexpr (VEC8) {
-    for (int d = lane * 8; d < D; d += 256) {
-      float a[8], p[8], n[8];
-      load8<T>(ea + d, a); load8<T>(epp + d, p); load8<T>(en + d, n);
-      if (normalize) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { a[k] = a[k] / na; p[k] = p[k] / np_; n[k] = n[k] / nn; }
+  if (lane == 0) {
+    if (loss) loss[li] = l;
+    // gradient bookkeeping: weight of this anchor and membership in the chains of its positive / negative row
+    float w2 = (l > 0.f) ? 2.f * (head_grad ? head_grad[li] : 1.f) : 0.f;       // relu'(0) = 0
+    if (wgt) {
+      wgt[li] = w2;
+      if (w2 != 0.f) {
+        const bool p_ok = !detach || (ip >= row_offset && ip < row_offset + B_local);
+        const bool n_ok = !detach || (in >= row_offset && in < row_offset + B_local);
+        if (p_ok) rnextp[li] = atomicExch(&rheadp[ip], (int32_t)li);
+        if (n_ok) rnextn[li] = atomicExch(&rheadn[in], (int32_t)li);
       }
-      float4* ga = reinterpret_cast<float4*>(dE + gi * D + d);
-      atomicAdd(ga, make_float4(w2 * (n[0] - p[0]), w2 * (n[1] - p[1]), w2 * (n[2] - p[2]), w2 * (n[3] - p[3])));
-      atomicAdd(ga + 1, make_float4(w2 * (n[4] - p[4]), w2 * (n[5] - p[5]), w2 * (n[6] - p[6]), w2 * (n[7] - p[7])));
-      if (p_ok) {
-        float4* gp = reinterpret_cast<float4*>(dE + (long)ip * D + d);
-        atomicAdd(gp, make_float4(w2 * (p[0] - a[0]), w2 * (p[1] - a[1]), w2 * (p[2] - a[2]), w2 * (p[3] - a[3])));
-        atomicAdd(gp + 1, make_float4(w2 * (p[4] - a[4]), w2 * (p[5] - a[5]), w2 * (p[6] - a[6]), w2 * (p[7] - a[7])));
-      }
-      if (n_ok) {
-        float4* gn = reinterpret_cast<float4*>(dE + (long)in * D + d);
-        atomicAdd(gn, make_float4(w2 * (a[0] - n[0]), w2 * (a[1] - n[1]), w2 * (a[2] - n[2]), w2 * (a[3] - n[3])));
-        atomicAdd(gn + 1, make_float4(w2 * (a[4] - n[4]), w2 * (a[5] - n[5]), w2 * (a[6] - n[6]), w2 * (a[7] - n[7])));
-      }
-    }
-  } else {
-    for (int d = lane; d < D; d += 32) {
-      float a = El<T>::to_f(ea[d]), p = El<T>::to_f(epp[d]), n = El<T>::to_f(en[d]);
-      if (normalize) { a = a / na; p = p / np_; n = n / nn; }
-      atomicAdd(&dE[gi * D + d], w2 * (n - p));
-      if (p_ok) atomicAdd(&dE[(long)ip * D + d], w2 * (p - a));
-      if (n_ok) atomicAdd(&dE[(long)in * D + d], w2 * (a - n));
     }
   }
 }
 
-template <typename T, bool VEC8>
-__global__ void __launch_bounds__(WARPS * 32)
-bh_norm_bwd_kernel(const T* __restrict__ E, const float* __restrict__ nrm, long B_all, int D, float* __restrict__ dE) {
-  const long row = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (row >= B_all) return;
-  const int lane = threadIdx.x & 31;
-  const float n = nrm[row];
-  float dot = 0.f;
-  if constexpr (VEC8) {
-    if (D <= 256) {                                  // one pass, row in registers
-      float x[8], gq[8];
-      const bool act = lane * 8 < D;
-      float4* gp = reinterpret_cast<float4*>(dE + row * D + lane * 8);
-      if (act) {
-        load8<T>(E + row * D + lane * 8, x);
-        const float4 g0 = gp[0], g1 = gp[1];
-        gq[0] = g0.x; gq[1] = g0.y; gq[2] = g0.z; gq[3] = g0.w; gq[4] = g1.x; gq[5] = g1.y; gq[6] = g1.z; gq[7] = g1.w;
+// ------------------------------------------------------------------------------------------ gradient (gather form)
+// One warp per row r of E_all: dX_r = [r is an active anchor] w_r (x_n - x_p) + sum_{j: p(j)=r} w_j (x_r - x_j)
+// + sum_{j: n(j)=r} w_j (x_j - x_r), then (normalize) dE_r = (dX_r - x_r (x_r . dX_r)) / |e_r|.  Every output row is
+// written exactly once with plain stores: no zero-fill, no floating-point atomics, no separate normalise-backward pass.
+template <typename T, int VEC>
+__device__ __forceinline__ void load_slab(const T* p, int d, int D, float inv, float (&o)[VEC]) {
+  if constexpr (VEC == 8) {
+    if (d < D) {
+      load8<T>(p + d, o);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { x[k] = x[k] / n; dot = fmaf(x[k], gq[k], dot); }
+      for (int k = 0; k < 8; ++k) o[k] = o[k] / inv;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    }
+  } else {
+    o[0] = d < D ? El<T>::to_f(p[d]) / inv : 0.f;
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(WARPS * 32)
+bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int normalize, long B_all, int D,
+               long row_offset, long B_local, const int32_t* __restrict__ idx_p, const int32_t* __restrict__ idx_n,
+               const float* __restrict__ wgt, const int32_t* __restrict__ rheadp, const int32_t* __restrict__ rheadn,
+               const int32_t* __restrict__ rnextp, const int32_t* __restrict__ rnextn, float* __restrict__ dE) {
+  const long r = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= B_all) return;
+  const int lane = threadIdx.x & 31;
+  const T* er = E + r * D;
+  const float nr = normalize ? nrm[r] : 1.f;
+  const long li = r - row_offset;
+  const bool anchor = li >= 0 && li < B_local;
+  const float wa = anchor ? wgt[li] : 0.f;
+  const int ap = wa != 0.f ? idx_p[li] : -1, an = wa != 0.f ? idx_n[li] : -1;
+  const int hp = rheadp[r], hn = rheadn[r];
+  constexpr int SLAB = 32 * VEC;
+  const bool single = D <= SLAB;
+  float dot = 0.f;
+  float acc[VEC], x[VEC];
+  for (int d0 = 0; d0 < D; d0 += SLAB) {
+    const int d = d0 + lane * VEC;
+    load_slab<T, VEC>(er, d, D, nr, x);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    if (wa != 0.f) {
+      float p[VEC], n[VEC];
+      load_slab<T, VEC>(E + (long)ap * D, d, D, normalize ? nrm[ap] : 1.f, p);
+      load_slab<T, VEC>(E + (long)an * D, d, D, normalize ? nrm[an] : 1.f, n);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = wa * (n[k] - p[k]);
+    }
+    for (int j = hp; j >= 0; j = rnextp[j]) {                        // r is the hardest positive of anchor j
+      const long a = row_offset + j;
+      float av[VEC];
+      load_slab<T, VEC>(E + a * D, d, D, normalize ? nrm[a] : 1.f, av);
+      const float w = wgt[j];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, x[k] - av[k], acc[k]);
+    }
+    for (int j = hn; j >= 0; j = rnextn[j]) {                        // r is the hardest negative of anchor j
+      const long a = row_offset + j;
+      float av[VEC];
+      load_slab<T, VEC>(E + a * D, d, D, normalize ? nrm[a] : 1.f, av);
+      const float w = wgt[j];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, av[k] - x[k], acc[k]);
+    }
+    if (normalize) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) dot = fmaf(x[k], acc[k], dot);
+    }
+    if (!(single && normalize) && d < D) {                           // raw dX (final if not normalising)
+      if constexpr (VEC == 8) {
+        float4* o = reinterpret_cast<float4*>(dE + r * D + d);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else {
+        dE[r * D + d] = acc[0];
       }
-      dot = warp_sum(dot);
-      if (act) {
-        gp[0] = make_float4((gq[0] - x[0] * dot) / n, (gq[1] - x[1] * dot) / n, (gq[2] - x[2] * dot) / n, (gq[3] - x[3] * dot) / n);
-        gp[1] = make_float4((gq[4] - x[4] * dot) / n, (gq[5] - x[5] * dot) / n, (gq[6] - x[6] * dot) / n, (gq[7] - x[7] * dot) / n);
-      }
-      return;
     }
   }
-  for (int d = lane; d < D; d += 32) dot = fmaf(El<T>::to_f(E[row * D + d]) / n, dE[row * D + d], dot);
+  if (!normalize) return;
   dot = warp_sum(dot);
-  for (int d = lane; d < D; d += 32) {
-    const float x = El<T>::to_f(E[row * D + d]) / n;
-    dE[row * D + d] = (dE[row * D + d] - x * dot) / n;
+  if (single) {
+    const int d = lane * VEC;
+    if (d < D) {
+      if constexpr (VEC == 8) {
+        float4* o = reinterpret_cast<float4*>(dE + r * D + d);
+        o[0] = make_float4((acc[0] - x[0] * dot) / nr, (acc[1] - x[1] * dot) / nr, (acc[2] - x[2] * dot) / nr, (acc[3] - x[3] * dot) / nr);
+        o[1] = make_float4((acc[4] - x[4] * dot) / nr, (acc[5] - x[5] * dot) / nr, (acc[6] - x[6] * dot) / nr, (acc[7] - x[7] * dot) / nr);
+      } else {
+        dE[r * D + d] = (acc[0] - x[0] * dot) / nr;
+      }
+    }
+    return;
+  }
+  for (int d0 = 0; d0 < D; d0 += SLAB) {                             // second pass over the raw dX row
+    const int d = d0 + lane * VEC;
+    if (d >= D) continue;
+    load_slab<T, VEC>(er, d, D, nr, x);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float* o = dE + r * D + d + k;
+      *o = (*o - x[k] * dot) / nr;
+    }
   }
 }
 
@@ -569,7 +630,10 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   EFM_REQUIRE(aligned(workspace, 256), EFM_E_ALIGN, "efm_bh_triplet_fwd_bwd: workspace must be 256-byte aligned");
   const BhLayout L = bh_layout(B_local, B_all, D, dtype, flags);
   EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_triplet_fwd_bwd: workspace %zu < required %zu", ws_bytes, L.total);
-  if (B_local == 0) return EFM_OK;
+  if (B_local == 0) {
+    if (dE_all) EFM_CUDA(cudaMemsetAsync(dE_all, 0, (size_t)B_all * D * 4, static_cast<cudaStream_t>(stream)));
+    return EFM_OK;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   auto* kpos = reinterpret_cast<unsigned long long*>(ws + L.kpos);
@@ -583,17 +647,21 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   int32_t* hhead = reinterpret_cast<int32_t*>(ws + L.hhead);
   int32_t* hnext = reinterpret_cast<int32_t*>(ws + L.hnext);
   int32_t* hslot = reinterpret_cast<int32_t*>(ws + L.hslot);
+  int32_t* rheadp = reinterpret_cast<int32_t*>(ws + L.rheadp);
+  int32_t* rheadn = reinterpret_cast<int32_t*>(ws + L.rheadn);
+  int32_t* rnextp = reinterpret_cast<int32_t*>(ws + L.rnextp);
+  int32_t* rnextn = reinterpret_cast<int32_t*>(ws + L.rnextn);
+  float* wgt = dE_all ? reinterpret_cast<float*>(ws + L.wgt) : nullptr;
   const int normalize = (flags & EFM_BH_NORMALIZE) ? 1 : 0;
   const int detach = (flags & EFM_BH_DETACH_GATHERED) ? 1 : 0;
   const unsigned grid_all = (unsigned)cdiv(B_all, WARPS), grid_loc = (unsigned)cdiv(B_local, WARPS);
   const bool vec = bh_vec8(E_all, D, dE_all);
 
-  if (L.use_tc)                                                   // empty label table: keys = ~0, heads = -1
-    EFM_CUDA(cudaMemsetAsync(ws + L.hkeys, 0xFF, (L.hhead - L.hkeys) + ((size_t)4 << L.tbits), st));
+  EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));     // empty label table + empty chains
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, labels_all, B_all, (int)D, L.Dp, normalize,
                                                           L.use_tc ? 1 : 0, L.xm_f32 ? 1 : 0, row_offset, B_local, sq, nrm,
-                                                          lab, xm_bf16, xm_f32, kpos, kneg, dE_all, hkeys, hhead, hnext,
+                                                          lab, xm_bf16, xm_f32, kpos, kneg, nullptr, hkeys, hhead, hnext,
                                                           hslot, L.tbits);
   });
   EFM_LAUNCH_CHECK("bh_prep");
@@ -605,21 +673,34 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
     bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
                                                               B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos,
                                                               kneg, xm_bf16, L.Dp, lab, hhead, hnext, hslot, loss, idx_p,
-                                                              idx_n, dE_all);
+                                                              idx_n, wgt, rheadp, rheadn, rnextp, rnextn);
   });
   EFM_LAUNCH_CHECK("bh_finalize");
-  if (dE_all && normalize) {
-    EFM_BH_DISPATCH(dtype, vec, T, V, {
-      bh_norm_bwd_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, B_all, (int)D, dE_all);
+  if (dE_all) {
+    EFM_DISPATCH_DTYPE(dtype, T, {
+      if (vec) bh_grad_kernel<T, 8><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
+                                                                      B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
+      else bh_grad_kernel<T, 1><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
+                                                                  B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
     });
-    EFM_LAUNCH_CHECK("bh_norm_bwd");
+    EFM_LAUNCH_CHECK("bh_grad");
   }
   return EFM_OK;
 }
 
 // Backward for given mined indices (head_grad per anchor): used when the loss vector was returned
-// un-reduced and autograd later supplies d(total)/d(loss_i).  workspace: 2 x B_all floats (row norms, scratch).
-extern "C" size_t efm_bh_backward_workspace_bytes(long B_all) { return align_up((size_t)(B_all > 0 ? B_all : 0) * 4, 256) * 2 + 1024; }
+// un-reduced and autograd later supplies d(total)/d(loss_i).
+struct BwdLayout { size_t nrm, sq, rheadp, rheadn, rnextp, rnextn, wgt, total; };
+static BwdLayout bwd_layout(long B_all) {
+  BwdLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t n = (size_t)(B_all > 0 ? B_all : 0) * 4;
+  L.nrm = take(n); L.sq = take(n); L.rheadp = take(n); L.rheadn = take(n); L.rnextp = take(n); L.rnextn = take(n); L.wgt = take(n);
+  L.total = off;
+  return L;
+}
+extern "C" size_t efm_bh_backward_workspace_bytes(long B_all) { return bwd_layout(B_all).total; }
 
 extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, long B_local, long D, int dtype,
                                float margin, const float* head_grad, int flags, const int32_t* idx_p,
@@ -628,18 +709,26 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
               "efm_bh_backward: bad shape B_all=%ld row_offset=%ld B_local=%ld D=%ld", B_all, row_offset, B_local, D);
   EFM_REQUIRE(E_all && idx_p && idx_n && dE_all && workspace, EFM_E_ARG, "efm_bh_backward: null pointer");
   EFM_REQUIRE(aligned(workspace, 256), EFM_E_ALIGN, "efm_bh_backward: workspace must be 256-byte aligned");
-  EFM_REQUIRE(ws_bytes >= efm_bh_backward_workspace_bytes(B_all), EFM_E_WORKSPACE, "efm_bh_backward: workspace too small");
+  const BwdLayout L = bwd_layout(B_all);
+  EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_backward: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* nrm = static_cast<float*>(workspace);
-  float* sq = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up((size_t)B_all * 4, 256));
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* nrm = reinterpret_cast<float*>(ws + L.nrm);
+  float* sq = reinterpret_cast<float*>(ws + L.sq);
+  int32_t* rheadp = reinterpret_cast<int32_t*>(ws + L.rheadp);
+  int32_t* rheadn = reinterpret_cast<int32_t*>(ws + L.rheadn);
+  int32_t* rnextp = reinterpret_cast<int32_t*>(ws + L.rnextp);
+  int32_t* rnextn = reinterpret_cast<int32_t*>(ws + L.rnextn);
+  float* wgt = reinterpret_cast<float*>(ws + L.wgt);
   const int normalize = (flags & EFM_BH_NORMALIZE) ? 1 : 0;
   const int detach = (flags & EFM_BH_DETACH_GATHERED) ? 1 : 0;
   const unsigned grid_all = (unsigned)cdiv(B_all, WARPS), grid_loc = (unsigned)cdiv(B_local, WARPS);
   const bool vec = bh_vec8(E_all, D, dE_all);
-  // row norms (if normalising) + zeroed dE in one pass: prep with every optional output disabled
+  EFM_CUDA(cudaMemsetAsync(ws + L.rheadp, 0xFF, L.rnextp - L.rheadp, st));
+  // row norms: prep with every optional output disabled
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nullptr, B_all, (int)D, (int)D, normalize, 0, 0, 0, 0,
-                                                          sq, nrm, nullptr, nullptr, nullptr, nullptr, nullptr, dE_all, nullptr,
+                                                          sq, nrm, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                           nullptr, nullptr, nullptr, 0);
   });
   EFM_LAUNCH_CHECK("bh_prep(stats)");
@@ -648,16 +737,18 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
       bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
                                                                 B_local, margin, head_grad, detach, 2, nullptr, nullptr, nullptr,
                                                                 0, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), dE_all);
+                                                                const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), wgt,
+                                                                rheadp, rheadn, rnextp, rnextn);
     });
     EFM_LAUNCH_CHECK("bh_finalize(bwd)");
   }
-  if (normalize) {
-    EFM_BH_DISPATCH(dtype, vec, T, V, {
-      bh_norm_bwd_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, B_all, (int)D, dE_all);
-    });
-    EFM_LAUNCH_CHECK("bh_norm_bwd");
-  }
+  EFM_DISPATCH_DTYPE(dtype, T, {
+    if (vec) bh_grad_kernel<T, 8><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
+                                                                    B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
+    else bh_grad_kernel<T, 1><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
+                                                                B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
+  });
+  EFM_LAUNCH_CHECK("bh_grad");
   return EFM_OK;
 }
 

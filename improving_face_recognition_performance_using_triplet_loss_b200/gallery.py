@@ -90,15 +90,22 @@ class Gallery:
         return i.reshape(-1), s.reshape(-1)
 
     def identify(self, Q: torch.Tensor, sim_th: float):
-        """Compare_Face_DB: person id of the global best row (-1 if nobody passes)."""
+        """Compare_Face_DB: persons are visited in ascending pid with a running strict maximum
+        (Feature.hpp:799-801), so the winner is the person of the best row and, among rows with EXACTLY the best
+        score, the lowest pid.  Returns (pid (nq,), best sim (nq,)); pid -1 if nobody passes.  Ties are resolved
+        among the 16 best rows (more than 16 bit-identical best scores would need a wider list)."""
         if self.person_ids is None:
             raise ValueError("identify() needs person_ids")
-        idx, sim = self.argmax(Q, sim_th)
-        local = torch.where(idx >= 0, idx - self.idx_base, idx).contiguous()
-        out = torch.empty_like(local)
+        K = min(L.GAL_MAX_K, self.N)
+        s, i = self.topk(Q, K, sim_th, positive_only=True)
+        local = torch.where(i >= 0, i - self.idx_base, i).contiguous()
+        pid = torch.empty_like(local)
         with torch.cuda.device(self.G.device):
-            L.check(L.lib.efm_gather_pid(L.ptr(local), L.ptr(self.person_ids), local.numel(), L.ptr(out), L.stream()))
-        return out, sim
+            L.check(L.lib.efm_gather_pid(L.ptr(local), L.ptr(self.person_ids), local.numel(), L.ptr(pid), L.stream()))
+        tied = (i >= 0) & (s == s[:, :1])
+        big = torch.iinfo(torch.int32).max
+        best = torch.where(tied, pid, torch.full_like(pid, big)).min(dim=1).values
+        return torch.where(best == big, torch.full_like(best, -1), best), s[:, 0]
 
 
 def merge_topk(part_scores: torch.Tensor, part_idx: torch.Tensor):
