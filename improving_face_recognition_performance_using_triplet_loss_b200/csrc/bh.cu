@@ -213,6 +213,7 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
 // chains (a handful of candidates per anchor).
 struct MineEpi {
   static constexpr int SMEM_PER_WARP = 0;
+  static constexpr int CW = 16;
   struct Params {
     const float* sq;          // |x_j|^2 of the mining rows, (B_all)
     const int32_t* labels;    // (B_all)
@@ -231,43 +232,45 @@ struct MineEpi {
     s.nbest = INFINITY;
     s.ngrp = -1;
   }
-  static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
-                                               const uint32_t (&acc)[32], int col0, float*) {
-    const int ncols = g.N - col0;                    // > 0 guaranteed by the caller
-    float pm[8];                                     // group-of-4 minima
-    if (ncols >= 32) {
-      const float4* sq4 = reinterpret_cast<const float4*>(p.sq + col0);
-      const int4* lb4 = reinterpret_cast<const int4*>(p.labels + col0);
+  // ragged right edge of the Gram (fewer than 16 valid columns): out of line, executed by at most one chunk per row block
+  static __device__ __noinline__ void chunk_tail(const float* sq, const int32_t* labels, int lab_i, const uint32_t (&acc)[16],
+                                                 int col0, int ncols, float& nbest, int& ngrp) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 s4 = __ldg(sq4 + q);
-        const int4 l4 = __ldg(lb4 + q);
-        const float v0 = fmaf(-2.f, __uint_as_float(acc[4 * q + 0]), (l4.x == s.lab_i) ? INFINITY : s4.x);
-        const float v1 = fmaf(-2.f, __uint_as_float(acc[4 * q + 1]), (l4.y == s.lab_i) ? INFINITY : s4.y);
-        const float v2 = fmaf(-2.f, __uint_as_float(acc[4 * q + 2]), (l4.z == s.lab_i) ? INFINITY : s4.z);
-        const float v3 = fmaf(-2.f, __uint_as_float(acc[4 * q + 3]), (l4.w == s.lab_i) ? INFINITY : s4.w);
-        pm[q] = fminf(fminf(fminf(v0, v1), v2), v3);                   // FMNMX3 + FMNMX
-      }
-    } else {
+    for (int q = 0; q < 4; ++q) {
+      float m4 = INFINITY;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float m4 = INFINITY;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = 4 * q + e;
-          if (k < ncols) {
-            const float sqv = (p.labels[col0 + k] == s.lab_i) ? INFINITY : p.sq[col0 + k];
-            m4 = fminf(m4, fmaf(-2.f, __uint_as_float(acc[k]), sqv));
-          }
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * q + e;
+        if (k < ncols) {
+          const float sqv = (labels[col0 + k] == lab_i) ? INFINITY : sq[col0 + k];
+          m4 = fminf(m4, fmaf(-2.f, __uint_as_float(acc[k]), sqv));
         }
-        pm[q] = m4;
       }
+      if (m4 < nbest) { nbest = m4; ngrp = col0 + 4 * q; }
     }
-    const float m = fminf(fminf(fminf(fminf(pm[0], pm[1]), pm[2]), fminf(fminf(pm[3], pm[4]), pm[5])), fminf(pm[6], pm[7]));
-    if (m < s.nbest) {                               // strict: the earlier group survives ties
-      int q = 7;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
+                                               const uint32_t (&acc)[16], int col0, float*) {
+    if (col0 + 16 > g.N) { chunk_tail(p.sq, p.labels, s.lab_i, acc, col0, g.N - col0, s.nbest, s.ngrp); return; }
+    const float4* sq4 = reinterpret_cast<const float4*>(p.sq + col0);
+    const int4* lb4 = reinterpret_cast<const int4*>(p.labels + col0);
+    float pm[4];                                     // group-of-4 minima
 #pragma unroll
-      for (int t = 6; t >= 0; --t) q = (pm[t] == m) ? t : q;
+    for (int q = 0; q < 4; ++q) {
+      const float4 s4 = __ldg(sq4 + q);
+      const int4 l4 = __ldg(lb4 + q);
+      const float v0 = fmaf(-2.f, __uint_as_float(acc[4 * q + 0]), (l4.x == s.lab_i) ? INFINITY : s4.x);
+      const float v1 = fmaf(-2.f, __uint_as_float(acc[4 * q + 1]), (l4.y == s.lab_i) ? INFINITY : s4.y);
+      const float v2 = fmaf(-2.f, __uint_as_float(acc[4 * q + 2]), (l4.z == s.lab_i) ? INFINITY : s4.z);
+      const float v3 = fmaf(-2.f, __uint_as_float(acc[4 * q + 3]), (l4.w == s.lab_i) ? INFINITY : s4.w);
+      pm[q] = fminf(fminf(fminf(v0, v1), v2), v3);                   // FMNMX3 + FMNMX
+    }
+    const float m = fminf(fminf(fminf(pm[0], pm[1]), pm[2]), pm[3]);
+    if (m < s.nbest) {                               // strict: the earlier group survives ties
+      int q = 3;
+      q = (pm[2] == m) ? 2 : q;
+      q = (pm[1] == m) ? 1 : q;
+      q = (pm[0] == m) ? 0 : q;
       s.nbest = m;
       s.ngrp = col0 + 4 * q;
     }

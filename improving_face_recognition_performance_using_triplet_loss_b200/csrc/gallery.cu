@@ -253,6 +253,7 @@ __global__ void recip_kernel(const float* __restrict__ x, long n, float* __restr
 // ------------------------------------------------------------------------------------------ tcgen05 top-K epilogue
 template <int KMAX> struct TopkEpi {
   static constexpr int SMEM_PER_WARP = 0;
+  static constexpr int CW = 16;
   struct Params {
     const float* gnorm;   // (N) stored gallery norms
     const float* rgn;     // (N) reciprocals
@@ -275,20 +276,20 @@ template <int KMAX> struct TopkEpi {
     s.tk.init();
   }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
-                                               const uint32_t (&acc)[32], int col0, float*) {
+                                               const uint32_t (&acc)[16], int col0, float*) {
     const int ncols = g.N - col0;
     float m = -INFINITY;
-    if (ncols >= 32) {
+    if (ncols >= 16) {
       const float4* r4 = reinterpret_cast<const float4*>(p.rgn + col0);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 4; ++q) {
         const float4 r = __ldg(r4 + q);
         m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(acc[4 * q]) * r.x, __uint_as_float(acc[4 * q + 1]) * r.y),
                            fmaxf(__uint_as_float(acc[4 * q + 2]) * r.z, __uint_as_float(acc[4 * q + 3]) * r.w)));
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
+      for (int k = 0; k < 16; ++k)
         if (k < ncols) m = fmaxf(m, __uint_as_float(acc[k]) * p.rgn[col0 + k]);
     }
     // conservative filter: can the chunk maximum enter the list?
@@ -296,17 +297,20 @@ template <int KMAX> struct TopkEpi {
     if (s.tk.full()) cut = fmaxf(cut, s.tk.s[KMAX - 1]);
     const float cand = m * s.rqn;
     if (!(cand >= cut - fabsf(cut) * 1e-5f - 1e-30f) && !(cand != cand)) return;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
       if (k < ncols) {
-        const float sim = __fdiv_rn(__uint_as_float(acc[k]), __fmul_rn(p.gnorm[col0 + k], s.qn));
+        float a = __uint_as_float(acc[0]);
+#pragma unroll
+        for (int t = 1; t < 16; ++t) a = (t == k) ? __uint_as_float(acc[t]) : a;
+        const float sim = __fdiv_rn(a, __fmul_rn(p.gnorm[col0 + k], s.qn));
         if (accept_score(sim, p.sim_th, p.flags)) s.tk.insert(sim, col0 + k);
       }
     }
   }
   static __device__ __forceinline__ void row_end(const Params& p, const tc::GramParams& g, int row, int, State& s) {
     if (!s.valid) return;
-    const int part = (int)(blockIdx.x % g.splits) * 2 + (int)(threadIdx.x >> 7);     // (split, column half)
+    const int part = (int)(blockIdx.x % g.splits) * tc::EPI_SLICES + (int)(threadIdx.x >> 7);   // (split, column slice)
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < p.K) {
@@ -320,7 +324,8 @@ template <int KMAX> struct TopkEpi {
 
 // ------------------------------------------------------------------------------------------ all-pairs cosine epilogue
 struct StoreEpi {
-  static constexpr int SMEM_PER_WARP = 32 * 33 * 4;
+  static constexpr int CW = 16;
+  static constexpr int SMEM_PER_WARP = 32 * 17 * 4;            // 32 rows x 16 columns (+1 pad) transpose tile
   struct Params {
     const float* rna;   // (M) 1/|a_i|
     const float* rnb;   // (N) 1/|b_j|
@@ -332,19 +337,22 @@ struct StoreEpi {
     s.row0 = row - (int)(threadIdx.x & 31);                   // first row of this warp's 32-row slab
   }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
-                                               const uint32_t (&acc)[32], int col0, float* scratch) {
+                                               const uint32_t (&acc)[16], int col0, float* scratch) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) scratch[lane * 33 + k] = __uint_as_float(acc[k]) * s.rna;
+    for (int k = 0; k < 16; ++k) scratch[lane * 17 + k] = __uint_as_float(acc[k]) * s.rna;
     __syncwarp();
-    const int col = col0 + lane;
+    // lanes 0-15 write row r, lanes 16-31 row r+16: two 64-byte segments per store instruction
+    const int c = lane & 15, rsel = lane >> 4;
+    const int col = col0 + c;
     if (col < g.N) {
       const float rb = p.rnb[col];
-      for (int r = 0; r < 32; ++r) {
-        const int orow = s.row0 + r;
-        if (orow >= g.M) break;
-        __stcs(&p.out[(long)orow * g.N + col], scratch[r * 33 + lane] * rb);
+#pragma unroll 4
+      for (int r = 0; r < 16; ++r) {
+        const int lr = r + 16 * rsel;
+        const int orow = s.row0 + lr;
+        if (orow < g.M) __stcs(&p.out[(long)orow * g.N + col], scratch[lr * 17 + c] * rb);
       }
     }
   }
@@ -431,7 +439,7 @@ extern "C" size_t efm_gallery_topk_workspace_bytes(long N, long D, long nq, int 
     off += align_up((size_t)exact_chunks(N) * nq * K * 4, 256) * 2;
     return off;
   }
-  const int parts_max = 2 * (int)cdiv(N, tc::BN);
+  const int parts_max = tc::EPI_SLICES * (int)cdiv(N, tc::BN);
   return topk_tc_layout(N, D, nq, K, parts_max).total;
 }
 
@@ -486,8 +494,8 @@ extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long 
   tc::GramParams g{};
   g.M = (int)nq; g.N = (int)N; g.nk = Kp / tc::BK;
   const int grid = tc::plan_gram(g, 1);
-  const int parts = g.splits * 2;
-  const TcOperands L = topk_tc_layout(N, D, nq, K, 2 * (int)cdiv(N, tc::BN));
+  const int parts = g.splits * tc::EPI_SLICES;
+  const TcOperands L = topk_tc_layout(N, D, nq, K, tc::EPI_SLICES * (int)cdiv(N, tc::BN));
   auto* gpad = reinterpret_cast<__nv_bfloat16*>(ws + L.gpad);
   auto* qpad = reinterpret_cast<__nv_bfloat16*>(ws + L.qpad);
   float* qn = reinterpret_cast<float*>(ws + L.qn);

@@ -3,8 +3,9 @@
 //
 //   G[i][j] = sum_k A[i][k] * B[j][k]      A: (M, Kp) bf16, B: (N, Kp) bf16, both K-major, fp32 accumulate
 //
-// One CTA = 10 warps: warps 0-7 epilogue (warp w reads TMEM lane quarter w%4, column half w/4),
-// warp 8 TMA producer (one elected lane), warp 9 MMA issuer (one elected lane) + TMEM owner.
+// One CTA = 18 warps: warps 0-15 epilogue (warp w reads TMEM lane quarter w%4, 64-column slice w/4; four
+// warps per scheduler hide the TMEM / L1 latencies of one another), warp 16 TMA producer (one elected lane),
+// warp 17 MMA issuer (one elected lane) + TMEM owner.
 // Tile = 128 rows x 256 columns x K (UMMA M=128, N=256, K=16, cta_group::1), accumulator
 // double-buffered in TMEM (2 x 256 columns = all 512), so the epilogue of tile t overlaps the MMAs of
 // tile t+1.  The A row-block (128 x Kp) stays resident in shared memory while the CTA walks its
@@ -22,10 +23,12 @@ namespace tc {
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_KB_BYTES = BM * BK * 2;   // 16 KB per K-block of the resident A row-block
 constexpr int B_ST_BYTES = BN * BK * 2;   // 32 KB per B stage
-constexpr int EPI_WARPS = 8;
-constexpr int PRODUCER_WARP = 8;
-constexpr int MMA_WARP = 9;
-constexpr int THREADS = 320;
+constexpr int EPI_WARPS = 16;             // 4 per TMEM lane quarter: each owns a 64-column slice of the tile
+constexpr int EPI_SLICES = EPI_WARPS / 4;
+constexpr int COLS_PER_WARP = BN / EPI_SLICES;
+constexpr int PRODUCER_WARP = EPI_WARPS;
+constexpr int MMA_WARP = EPI_WARPS + 1;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_NK = 8;                 // K <= 512
 constexpr int TMEM_COLS = 512;
@@ -134,6 +137,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait + make the destination registers data-dependent on the wait, so no consumer can be scheduled above it
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
@@ -172,11 +193,12 @@ inline int pick_stages(int nk, int extra) {
 // Epi supplies:  struct Params;  struct State;
 //   static __device__ void row_begin(const Params&, const GramParams&, int row, State&);
 //   static constexpr int SMEM_PER_WARP;   (bytes of scratch shared memory per epilogue warp, may be 0)
-//   static __device__ void chunk(const Params&, const GramParams&, State&, int row, const uint32_t (&acc)[32], int col0,
+//   static constexpr int CW;              (16 or 32: columns per TMEM load / chunk)
+//   static __device__ void chunk(const Params&, const GramParams&, State&, int row, const uint32_t (&acc)[CW], int col0,
 //                                float* scratch);
 //   static __device__ void row_end(const Params&, const GramParams&, int row, int part, State&);
 // row = anchor/query row index of this thread, col0 = first Gram column of the 32-column chunk held in
-// acc (fp32 bit patterns); part = ordinal of (CTA, column half) for partial-result slots.
+// acc (fp32 bit patterns); part = this warp's column slice (0..3) for partial-result slots.
 template <class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams g,
@@ -267,12 +289,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ---------------- epilogue warps ----------------
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, slice = warp >> 2;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     int acc = 0; uint32_t acc_phase = 0; int cur_rb = -1;
     typename Epi::State st;
     int row = 0;
-    const int part = (int)blockIdx.x * 2 + half;
+    const int part = slice;
+    constexpr int CW = Epi::CW;                                      // columns per TMEM load / epilogue chunk
     for (long t = t0; t < t1; ++t) {
       const int rb = (int)(t / CT), ct = (int)(t % CT);
       if (rb != cur_rb) {
@@ -283,28 +306,16 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * BN + half * (BN / 2));
-      const int colh = ct * BN + half * (BN / 2);                    // first column of this warp's half tile
-      // 4 chunks of 32 columns, TMEM loads software-pipelined: chunk c+1 is in flight while chunk c is consumed
-      uint32_t va[32], vb[32];
-      if (colh < g.N) {                                              // warp-uniform
-        tmem_ld32(t_acc, va);
-        tmem_ld_wait(va);
-        if (colh + 32 < g.N) tmem_ld32(t_acc + 32, vb);
-        Epi::chunk(ep, g, st, row, va, colh, scratch);
-        if (colh + 32 < g.N) {
-          tmem_ld_wait(vb);
-          if (colh + 64 < g.N) tmem_ld32(t_acc + 64, va);
-          Epi::chunk(ep, g, st, row, vb, colh + 32, scratch);
-          if (colh + 64 < g.N) {
-            tmem_ld_wait(va);
-            if (colh + 96 < g.N) tmem_ld32(t_acc + 96, vb);
-            Epi::chunk(ep, g, st, row, va, colh + 64, scratch);
-            if (colh + 96 < g.N) {
-              tmem_ld_wait(vb);
-              Epi::chunk(ep, g, st, row, vb, colh + 96, scratch);
-            }
-          }
+      const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * BN + slice * COLS_PER_WARP);
+      const int colw = ct * BN + slice * COLS_PER_WARP;              // first column of this warp's slice
+#pragma unroll
+      for (int c = 0; c < COLS_PER_WARP / CW; ++c) {
+        const int col0 = colw + c * CW;
+        if (col0 < g.N) {                                            // warp-uniform
+          uint32_t v[CW];
+          tmem_ld(t_acc + c * CW, v);
+          tmem_ld_wait(v);
+          Epi::chunk(ep, g, st, row, v, col0, scratch);
         }
       }
       tc_fence_before();
