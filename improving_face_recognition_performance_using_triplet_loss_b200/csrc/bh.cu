@@ -37,9 +37,10 @@ BhLayout bh_layout(long B_local, long B_all, long D, int dtype, int flags) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.kpos = take((size_t)B_local * 8);
   L.kneg = take((size_t)B_local * 8);
-  L.sq = take((size_t)B_all * 4);
+  const size_t Bpad = (size_t)cdiv(B_all, tc::BN) * tc::BN;  // sq/labels padded to whole column tiles (sq = +inf there)
+  L.sq = take(Bpad * 4);
   L.nrm = take((size_t)B_all * 4);
-  L.lab = take((size_t)B_all * 4);
+  L.lab = take(Bpad * 4);
   L.xm = take(L.use_tc ? (size_t)B_all * L.Dp * 2 : (L.xm_f32 ? (size_t)B_all * D * 4 : 0));
   // per-label chains (tensor-core path): open-addressing table of (label -> head row), next pointers, slot per row
   // one memset(0xFF) resets [hkeys | hhead | rheadp | rheadn]: empty label table, empty chains (-1 heads)
@@ -186,7 +187,12 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
     sq[row] = s2;
     nrm[row] = n;
     const int32_t lab = labels ? labels[row] : 0;
-    if (lab_ws) lab_ws[row] = lab;
+    if (lab_ws) {
+      lab_ws[row] = lab;
+      // columns beyond B_all inside the last Gram tile: |x|^2 = +inf so they can never be mined (no edge path in the kernel)
+      const long Bpad = (B_all + tc::BN - 1) / tc::BN * tc::BN;
+      for (long j = B_all + row; j < Bpad; j += B_all) { sq[j] = INFINITY; lab_ws[j] = 0; }
+    }
     const long li = row - row_offset;
     if (kpos && li >= 0 && li < B_local) { kpos[li] = KEY_POS_EMPTY; kneg[li] = KEY_NEG_EMPTY; }
     if (hkeys) {                                     // push this row on its label's chain
@@ -232,26 +238,9 @@ struct MineEpi {
     s.nbest = INFINITY;
     s.ngrp = -1;
   }
-  // ragged right edge of the Gram (fewer than 16 valid columns): out of line, executed by at most one chunk per row block
-  static __device__ __noinline__ void chunk_tail(const float* sq, const int32_t* labels, int lab_i, const uint32_t (&acc)[16],
-                                                 int col0, int ncols, float& nbest, int& ngrp) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float m4 = INFINITY;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = 4 * q + e;
-        if (k < ncols) {
-          const float sqv = (labels[col0 + k] == lab_i) ? INFINITY : sq[col0 + k];
-          m4 = fminf(m4, fmaf(-2.f, __uint_as_float(acc[k]), sqv));
-        }
-      }
-      if (m4 < nbest) { nbest = m4; ngrp = col0 + 4 * q; }
-    }
-  }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
                                                const uint32_t (&acc)[16], int col0, float*) {
-    if (col0 + 16 > g.N) { chunk_tail(p.sq, p.labels, s.lab_i, acc, col0, g.N - col0, s.nbest, s.ngrp); return; }
+    // no edge handling: sq/labels are padded to whole tiles with |x|^2 = +inf and TMA zero-fills the Gram there
     const float4* sq4 = reinterpret_cast<const float4*>(p.sq + col0);
     const int4* lb4 = reinterpret_cast<const int4*>(p.labels + col0);
     float pm[4];                                     // group-of-4 minima
