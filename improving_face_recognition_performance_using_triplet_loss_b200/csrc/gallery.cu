@@ -263,6 +263,7 @@ template <int KMAX> struct TopkEpi {
     long idx_base, nq;
     float* part_s;        // (parts, nq, K)
     int32_t* part_i;
+    int col_slices;       // 64-column slices per row half (4 for the 128x256 shape, 2 for 256x128)
   };
   struct State {
     TopK<KMAX> tk;
@@ -308,9 +309,9 @@ template <int KMAX> struct TopkEpi {
       }
     }
   }
-  static __device__ __forceinline__ void row_end(const Params& p, const tc::GramParams& g, int row, int, State& s) {
+  static __device__ __forceinline__ void row_end(const Params& p, const tc::GramParams& g, int row, int cs, State& s) {
     if (!s.valid) return;
-    const int part = (int)(blockIdx.x % g.splits) * tc::EPI_SLICES + (int)(threadIdx.x >> 7);   // (split, column slice)
+    const int part = (int)(blockIdx.x % g.splits) * p.col_slices + cs;                          // (split, column slice)
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < p.K) {
@@ -444,9 +445,9 @@ extern "C" size_t efm_gallery_topk_workspace_bytes(long N, long D, long nq, int 
 }
 
 template <int KMAX>
-static int topk_tc_launch(const void* Gp, const void* Qp, tc::GramParams g, int grid,
+static int topk_tc_launch(const void* Gp, const void* Qp, int mh, tc::GramParams g, int grid,
                           const typename TopkEpi<KMAX>::Params& ep, cudaStream_t st) {
-  return tc::launch_gram<TopkEpi<KMAX>>(Qp, Gp, g, ep, grid, st);
+  return tc::launch_gram<TopkEpi<KMAX>>(Qp, Gp, mh, g, ep, grid, st);
 }
 
 extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long D, const void* Q, long nq, int K,
@@ -493,8 +494,10 @@ extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long 
   EFM_REQUIRE(Kp <= tc::MAX_NK * tc::BK, EFM_E_UNSUPPORTED, "efm_gallery_topk: D=%ld > %d on the tensor-core path", D, tc::MAX_NK * tc::BK);
   tc::GramParams g{};
   g.M = (int)nq; g.N = (int)N; g.nk = Kp / tc::BK;
-  const int grid = tc::plan_gram(g, 1);
-  const int parts = g.splits * tc::EPI_SLICES;
+  const int mh = tc::pick_mh(g.M, g.nk);
+  const int grid = tc::plan_gram(g, mh, 1);
+  const int col_slices = tc::EPI_SLICES / mh;
+  const int parts = g.splits * col_slices;
   const TcOperands L = topk_tc_layout(N, D, nq, K, tc::EPI_SLICES * (int)cdiv(N, tc::BN));
   auto* gpad = reinterpret_cast<__nv_bfloat16*>(ws + L.gpad);
   auto* qpad = reinterpret_cast<__nv_bfloat16*>(ws + L.qpad);
@@ -517,14 +520,14 @@ extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long 
   const void* Gop = copy_g ? (const void*)gpad : G;
   int rc;
   if (K == 1) {
-    TopkEpi<1>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi};
-    rc = topk_tc_launch<1>(Gop, qpad, g, grid, ep, st);
+    TopkEpi<1>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
+    rc = topk_tc_launch<1>(Gop, qpad, mh, g, grid, ep, st);
   } else if (K <= 8) {
-    TopkEpi<8>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi};
-    rc = topk_tc_launch<8>(Gop, qpad, g, grid, ep, st);
+    TopkEpi<8>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
+    rc = topk_tc_launch<8>(Gop, qpad, mh, g, grid, ep, st);
   } else {
-    TopkEpi<EFM_GAL_MAX_K>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi};
-    rc = topk_tc_launch<EFM_GAL_MAX_K>(Gop, qpad, g, grid, ep, st);
+    TopkEpi<EFM_GAL_MAX_K>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
+    rc = topk_tc_launch<EFM_GAL_MAX_K>(Gop, qpad, mh, g, grid, ep, st);
   }
   if (rc) return rc;
   topk_merge_kernel<<<(unsigned)cdiv(nq, 8), 256, 0, st>>>(ps, pi, parts, nq, K, K, out_score, out_idx);
@@ -575,8 +578,8 @@ extern "C" int efm_cosine_allpairs(const void* A, const void* B, long M, long N,
   EFM_LAUNCH_CHECK("pad_rows");
   tc::GramParams g{};
   g.M = (int)M; g.N = (int)N; g.nk = Kp / tc::BK;
-  const int grid = tc::plan_gram(g, 0, StoreEpi::SMEM_PER_WARP * tc::EPI_WARPS);
-  EFM_REQUIRE(g.stages >= 2, EFM_E_UNSUPPORTED, "efm_cosine_allpairs: D=%ld leaves no room for the B pipeline", D);
+  const int mh = tc::pick_mh(g.M, g.nk);
+  const int grid = tc::plan_gram(g, mh, 0, StoreEpi::SMEM_PER_WARP * tc::EPI_WARPS);
   StoreEpi::Params ep{rna, rnb, out};
-  return tc::launch_gram<StoreEpi>(apad, bpad, g, ep, grid, st);
+  return tc::launch_gram<StoreEpi>(apad, bpad, mh, g, ep, grid, st);
 }

@@ -20,16 +20,26 @@
 namespace efm {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int A_KB_BYTES = BM * BK * 2;   // 16 KB per K-block of the resident A row-block
-constexpr int B_ST_BYTES = BN * BK * 2;   // 32 KB per B stage
+// Two tile shapes, selected by the template parameter MH (number of 128-row UMMA halves per CTA tile):
+//   MH = 1: 128 rows x 256 columns  (A block 16 KB / K-block, B stage 32 KB)   -- any K <= 512
+//   MH = 2: 256 rows x 128 columns  (A block 32 KB / K-block, B stage 16 KB)   -- K <= 256; halves the bytes
+//           every SM must pull from L2 per MAC (the 128 x 256 shape is bound by the per-SM L2 port)
+// Either way the CTA tile is 32768 accumulators = 2 x 256 TMEM columns with double buffering.
+constexpr int BK = 64;
+template <int MH> struct Shape {
+  static constexpr int BM = 128 * MH;
+  static constexpr int BN = 256 / MH;
+  static constexpr int A_KB_BYTES = BM * BK * 2;
+  static constexpr int B_ST_BYTES = BN * BK * 2;
+};
+constexpr int BM = 128, BN = 256;          // MH = 1 shape (host-side padding granularity)
 constexpr int EPI_WARPS = 16;             // 4 per TMEM lane quarter: each owns a 64-column slice of the tile
 constexpr int EPI_SLICES = EPI_WARPS / 4;
-constexpr int COLS_PER_WARP = BN / EPI_SLICES;
+constexpr int COLS_PER_WARP = 64;          // BN / (EPI_SLICES / MH) for both shapes
 constexpr int PRODUCER_WARP = EPI_WARPS;
 constexpr int MMA_WARP = EPI_WARPS + 1;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int MAX_NK = 8;                 // K <= 512
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;        // 227 KB opt-in maximum per CTA
@@ -108,8 +118,8 @@ constexpr uint64_t SMEM_DESC_BASE = (uint64_t(1) << 16)              // leading 
                                     | (uint64_t(2) << 61);           // SWIZZLE_128B
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) { return SMEM_DESC_BASE | uint64_t((addr & 0x3FFFFu) >> 4); }
 
-// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, N=256, M=128
-constexpr uint32_t IDESC_BF16_M128_N256 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N given
+__host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(128 >> 4) << 24); }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -181,11 +191,11 @@ __device__ __forceinline__ void tile_range(const GramParams& g, long& t0, long& 
   }
 }
 
-inline size_t smem_bytes(int nk, int stages, int extra) {
-  return 1024 /*alignment slack*/ + (size_t)nk * A_KB_BYTES + (size_t)stages * B_ST_BYTES + 256 /*barriers*/ + extra;
+template <int MH> inline size_t smem_bytes(int nk, int stages, int extra) {
+  return 1024 /*alignment slack*/ + (size_t)nk * Shape<MH>::A_KB_BYTES + (size_t)stages * Shape<MH>::B_ST_BYTES + 256 /*barriers*/ + extra;
 }
-inline int pick_stages(int nk, int extra) {
-  int s = (int)((SMEM_LIMIT - 1024 - 256 - extra - (long)nk * A_KB_BYTES) / B_ST_BYTES);
+template <int MH> inline int pick_stages(int nk, int extra) {
+  int s = (int)((SMEM_LIMIT - 1024 - 256 - extra - (long)nk * Shape<MH>::A_KB_BYTES) / Shape<MH>::B_ST_BYTES);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 
@@ -199,10 +209,14 @@ inline int pick_stages(int nk, int extra) {
 //   static __device__ void row_end(const Params&, const GramParams&, int row, int part, State&);
 // row = anchor/query row index of this thread, col0 = first Gram column of the 32-column chunk held in
 // acc (fp32 bit patterns); part = this warp's column slice (0..3) for partial-result slots.
-template <class Epi>
+template <class Epi, int MH>
 __global__ void __launch_bounds__(THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams g,
             const typename Epi::Params ep) {
+  constexpr int BM = Shape<MH>::BM, BN = Shape<MH>::BN;
+  constexpr int A_KB_BYTES = Shape<MH>::A_KB_BYTES, B_ST_BYTES = Shape<MH>::B_ST_BYTES;
+  constexpr int ACC_COLS = 256;                                      // TMEM columns per accumulator buffer (MH * BN)
+  constexpr uint32_t IDESC = idesc_bf16_m128(BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t sA = base;
@@ -270,14 +284,18 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);           // epilogue drained this accumulator
         tc_fence_after();
         if (rb != cur_rb) { mbar_wait(bar_a_full, a_full_phase); a_full_phase ^= 1; cur_rb = rb; }
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
         for (int kb = 0; kb < g.nk; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t a0 = sA + kb * A_KB_BYTES, b0 = sB + stage * B_ST_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, smem_desc(a0 + k * 32), smem_desc(b0 + k * 32), IDESC_BF16_M128_N256, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+            for (int h = 0; h < MH; ++h)                             // row half h: A rows [128h, 128h+128) -> TMEM columns [h*BN, +BN)
+              umma_bf16(d_tmem + h * BN, smem_desc(a0 + h * (128 * BK * 2) + k * 32), smem_desc(b0 + k * 32), IDESC,
+                        (kb | k) ? 1u : 0u);
+          }
           umma_commit(bar_empty + 8 * stage);                        // stage reusable once these MMAs retire
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
@@ -289,25 +307,27 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ---------------- epilogue warps ----------------
+    constexpr int COL_SLICES = EPI_SLICES / MH;                      // column slices of 64 per row half
     const int quarter = warp & 3, slice = warp >> 2;
+    const int rowhalf = slice / COL_SLICES, cs = slice % COL_SLICES;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     int acc = 0; uint32_t acc_phase = 0; int cur_rb = -1;
     typename Epi::State st;
     int row = 0;
-    const int part = slice;
+    const int part = cs;
     constexpr int CW = Epi::CW;                                      // columns per TMEM load / epilogue chunk
     for (long t = t0; t < t1; ++t) {
       const int rb = (int)(t / CT), ct = (int)(t % CT);
       if (rb != cur_rb) {
         if (cur_rb >= 0) Epi::row_end(ep, g, row, part, st);
-        row = rb * BM + quarter * 32 + lane;
+        row = rb * BM + rowhalf * 128 + quarter * 32 + lane;
         Epi::row_begin(ep, g, row, st);
         cur_rb = rb;
       }
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * BN + slice * COLS_PER_WARP);
-      const int colw = ct * BN + slice * COLS_PER_WARP;              // first column of this warp's slice
+      const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + rowhalf * BN + cs * COLS_PER_WARP);
+      const int colw = ct * BN + cs * COLS_PER_WARP;                 // first column of this warp's slice
 #pragma unroll
       for (int c = 0; c < COLS_PER_WARP / CW; ++c) {
         const int col0 = colw + c * CW;
@@ -336,29 +356,33 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // 2-D bf16 row-major (rows, Kp) tensor map with a (64 x box_rows) box, SWIZZLE_128B, zero OOB fill.
 int make_tmap_bf16(CUtensorMap* out, const void* base, long rows, long Kp, int box_rows);
 
-template <class Epi>
-int launch_gram(const void* A, const void* B, GramParams g, const typename Epi::Params& ep, int grid, cudaStream_t st) {
+template <class Epi, int MH>
+int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Epi::Params& ep, int grid, cudaStream_t st) {
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, BM);
+  int rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, Shape<MH>::BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tmB, B, g.N, (long)g.nk * BK, BN);
+  rc = make_tmap_bf16(&tmB, B, g.N, (long)g.nk * BK, Shape<MH>::BN);
   if (rc) return rc;
-  const size_t smem = smem_bytes(g.nk, g.stages, Epi::SMEM_PER_WARP * EPI_WARPS);
+  const size_t smem = smem_bytes<MH>(g.nk, g.stages, Epi::SMEM_PER_WARP * EPI_WARPS);
   static bool attr_done = false;                                     // per instantiation
   if (!attr_done) {
-    EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
-  gram_kernel<Epi><<<grid, THREADS, smem, st>>>(tmA, tmB, g, ep);
+  gram_kernel<Epi, MH><<<grid, THREADS, smem, st>>>(tmA, tmB, g, ep);
   EFM_LAUNCH_CHECK("gram_kernel");
   return EFM_OK;
 }
 
+// tile shape: the 256 x 128 shape whenever the resident A block fits (K <= 256) and there are at least 256 rows
+inline int pick_mh(int M, int nk) { return (nk <= 4 && M > 128) ? 2 : 1; }
+
 // fills row_blocks / col_tiles / stages / schedule and returns the grid size
-inline int plan_gram(GramParams& g, int sched_mode, int smem_extra = 0) {
-  g.row_blocks = (int)cdiv(g.M, BM);
-  g.col_tiles = (int)cdiv(g.N, BN);
-  g.stages = pick_stages(g.nk, smem_extra);
+inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0) {
+  const int bm = 128 * mh, bn = 256 / mh;
+  g.row_blocks = (int)cdiv(g.M, bm);
+  g.col_tiles = (int)cdiv(g.N, bn);
+  g.stages = mh == 2 ? pick_stages<2>(g.nk, smem_extra) : pick_stages<1>(g.nk, smem_extra);
   g.sched_mode = sched_mode;
   const long T = (long)g.row_blocks * g.col_tiles;
   const int sms = num_sms();
@@ -372,6 +396,14 @@ inline int plan_gram(GramParams& g, int sched_mode, int smem_extra = 0) {
   if (splits < 1) splits = 1;
   g.splits = splits;
   return g.row_blocks * splits;
+}
+
+template <class Epi>
+int launch_gram(const void* A, const void* B, int mh, const GramParams& g, const typename Epi::Params& ep, int grid,
+                cudaStream_t st) {
+  EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "gram: K = %d leaves no shared memory for the B pipeline", g.nk * BK);
+  if (mh == 2) return launch_gram_mh<Epi, 2>(A, B, g, ep, grid, st);
+  return launch_gram_mh<Epi, 1>(A, B, g, ep, grid, st);
 }
 
 }  // namespace tc
