@@ -14,6 +14,7 @@
 // from TMEM registers.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -45,6 +46,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;        // 227 KB opt-in maximum per CTA
 
 struct GramParams {
+  int debug;             // profiling aid (env EFM_GRAM_DEBUG): 1 = skip the epilogue work, 2 = TMEM loads only
   int M, N;              // valid rows of A / rows of B (= Gram columns)
   int nk;                // K blocks of 64 (Kp = 64 * nk)
   int stages;            // B ring depth
@@ -65,25 +67,38 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires), so waiting warps do not burn issue slots of the warps that share their scheduler.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(200000u)
+      : "memory");
+  return done;
+}
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("efmtl: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 // Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (it == 64) t0 = clock64();
-    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) {   // ~2 s
-      printf("efmtl: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > 20000u) mbar_timeout(bar, parity);               // >= ~2 s of hardware sleeps
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -252,58 +267,75 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  long t0, t1;
-  tile_range(g, t0, t1);
+  long t0l, t1l;
+  tile_range(g, t0l, t1l);
   const int CT = g.col_tiles;
+  const int ntiles = (int)(t1l - t0l);
+  const int rb0 = (int)(t0l / CT), ct0 = (int)(t0l % CT);           // the only divisions; tiles advance incrementally
 
   if (warp == PRODUCER_WARP) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, a_empty_phase = 0; int cur_rb = -1;
-      for (long t = t0; t < t1; ++t) {
-        const int rb = (int)(t / CT), ct = (int)(t % CT);
-        if (rb != cur_rb) {
-          if (cur_rb >= 0) { mbar_wait(bar_a_empty, a_empty_phase); a_empty_phase ^= 1; }
+    // whole warp runs the (warp-uniform) loop so counters live in uniform registers; one elected lane issues
+    const uint32_t leader = elect_one();
+    int stage = 0; uint32_t phase = 0, a_empty_phase = 0;
+    int rb = rb0, ct = ct0;
+    for (int i = 0; i < ntiles; ++i) {
+      if (i == 0 || ct == 0) {                                       // new row block: (re)load the resident A block
+        if (i != 0) { mbar_wait(bar_a_empty, a_empty_phase); a_empty_phase ^= 1; }
+        if (leader) {
           mbar_expect_tx(bar_a_full, (uint32_t)g.nk * A_KB_BYTES);
           for (int kb = 0; kb < g.nk; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, bar_a_full, kb * BK, rb * BM);
-          cur_rb = rb;
-        }
-        for (int kb = 0; kb < g.nk; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          mbar_expect_tx(bar_full + 8 * stage, B_ST_BYTES);
-          tma_load_2d(sB + stage * B_ST_BYTES, &tmB, bar_full + 8 * stage, kb * BK, ct * BN);
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
+      for (int kb = 0; kb < g.nk; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (leader) {
+          if (g.debug & 4) { mbar_arrive(bar_full + 8 * stage); }    // profiling: no B traffic
+          else {
+            mbar_expect_tx(bar_full + 8 * stage, B_ST_BYTES);
+            tma_load_2d(sB + stage * B_ST_BYTES, &tmB, bar_full + 8 * stage, kb * BK, ct * BN);
+          }
+        }
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++ct == CT) { ct = 0; ++rb; }
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, a_full_phase = 0; int cur_rb = -1;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (long t = t0; t < t1; ++t) {
-        const int rb = (int)(t / CT);
-        mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);           // epilogue drained this accumulator
+    const uint32_t leader = elect_one();
+    int stage = 0; uint32_t phase = 0, a_full_phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    int ct = ct0;
+    const uint64_t descA0 = smem_desc(sA), descB0 = smem_desc(sB);
+    for (int i = 0; i < ntiles; ++i) {
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);             // epilogue drained this accumulator
+      if (i == 0 || ct == 0) { mbar_wait(bar_a_full, a_full_phase); a_full_phase ^= 1; }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
+      for (int kb = 0; kb < g.nk; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        if (rb != cur_rb) { mbar_wait(bar_a_full, a_full_phase); a_full_phase ^= 1; cur_rb = rb; }
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
-        for (int kb = 0; kb < g.nk; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t a0 = sA + kb * A_KB_BYTES, b0 = sB + stage * B_ST_BYTES;
+        if (leader) {
+          const uint64_t da = descA0 + (uint64_t)((kb * A_KB_BYTES) >> 4);
+          const uint64_t db = descB0 + (uint64_t)((stage * B_ST_BYTES) >> 4);
+          if (!(g.debug & 8)) {                                      // profiling: no MMA issue
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
+            for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-            for (int h = 0; h < MH; ++h)                             // row half h: A rows [128h, 128h+128) -> TMEM columns [h*BN, +BN)
-              umma_bf16(d_tmem + h * BN, smem_desc(a0 + h * (128 * BK * 2) + k * 32), smem_desc(b0 + k * 32), IDESC,
-                        (kb | k) ? 1u : 0u);
+              for (int h = 0; h < MH; ++h)                           // row half h: A rows [128h, +128) -> TMEM columns [h*BN, +BN)
+                umma_bf16(d_tmem + h * BN, da + (uint64_t)((h * (128 * BK * 2) + k * 32) >> 4), db + (uint64_t)((k * 32) >> 4),
+                          IDESC, (kb | k) ? 1u : 0u);
+            }
           }
           umma_commit(bar_empty + 8 * stage);                        // stage reusable once these MMAs retire
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_acc_full + 8 * acc);                         // accumulator ready for the epilogue
-        const bool last_of_rb = (t + 1 == t1) || ((int)((t + 1) / CT) != rb);
-        if (last_of_rb) umma_commit(bar_a_empty);                    // A row-block may be overwritten
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
+      const bool last_of_rb = (i + 1 == ntiles) || (ct + 1 == CT);
+      if (leader) {
+        umma_commit(bar_acc_full + 8 * acc);                         // accumulator ready for the epilogue
+        if (last_of_rb) umma_commit(bar_a_empty);                    // A row-block may be overwritten
+      }
+      if (++ct == CT) ct = 0;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ---------------- epilogue warps ----------------
@@ -311,39 +343,41 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quarter = warp & 3, slice = warp >> 2;
     const int rowhalf = slice / COL_SLICES, cs = slice % COL_SLICES;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    int acc = 0; uint32_t acc_phase = 0; int cur_rb = -1;
+    int acc = 0; uint32_t acc_phase = 0;
     typename Epi::State st;
     int row = 0;
     const int part = cs;
     constexpr int CW = Epi::CW;                                      // columns per TMEM load / epilogue chunk
-    for (long t = t0; t < t1; ++t) {
-      const int rb = (int)(t / CT), ct = (int)(t % CT);
-      if (rb != cur_rb) {
-        if (cur_rb >= 0) Epi::row_end(ep, g, row, part, st);
+    int rb = rb0, ct = ct0;
+    for (int i = 0; i < ntiles; ++i) {
+      if (i == 0 || ct == 0) {
+        if (i != 0) Epi::row_end(ep, g, row, part, st);
         row = rb * BM + rowhalf * 128 + quarter * 32 + lane;
         Epi::row_begin(ep, g, row, st);
-        cur_rb = rb;
       }
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + rowhalf * BN + cs * COLS_PER_WARP);
       const int colw = ct * BN + cs * COLS_PER_WARP;                 // first column of this warp's slice
+      if ((g.debug & 3) != 1) {
 #pragma unroll
-      for (int c = 0; c < COLS_PER_WARP / CW; ++c) {
-        const int col0 = colw + c * CW;
-        if (col0 < g.N) {                                            // warp-uniform
-          uint32_t v[CW];
-          tmem_ld(t_acc + c * CW, v);
-          tmem_ld_wait(v);
-          Epi::chunk(ep, g, st, row, v, col0, scratch);
+        for (int c = 0; c < COLS_PER_WARP / CW; ++c) {
+          const int col0 = colw + c * CW;
+          if (col0 < g.N) {                                          // warp-uniform
+            uint32_t v[CW];
+            tmem_ld(t_acc + c * CW, v);
+            tmem_ld_wait(v);
+            if ((g.debug & 3) != 2) Epi::chunk(ep, g, st, row, v, col0, scratch);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++ct == CT) { ct = 0; ++rb; }
     }
-    if (cur_rb >= 0) Epi::row_end(ep, g, row, part, st);
+    if (ntiles > 0) Epi::row_end(ep, g, row, part, st);
   }
 
   tc_fence_before();
@@ -375,14 +409,22 @@ int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Ep
 }
 
 // tile shape: the 256 x 128 shape whenever the resident A block fits (K <= 256) and there are at least 256 rows
-inline int pick_mh(int M, int nk) { return (nk <= 4 && M > 128) ? 2 : 1; }
+inline int pick_mh(int M, int nk) {
+  if (const char* e = getenv("EFM_GRAM_MH")) { const int v = atoi(e); if (v == 1 || (v == 2 && nk <= 4)) return v; }
+  return (nk <= 4 && M > 128) ? 2 : 1;
+}
 
 // fills row_blocks / col_tiles / stages / schedule and returns the grid size
 inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0) {
   const int bm = 128 * mh, bn = 256 / mh;
+  { const char* e = getenv("EFM_GRAM_DEBUG"); g.debug = e ? atoi(e) : 0; }
+  g.stages = 0;
+  if (const char* e = getenv("EFM_GRAM_STAGES")) { const int v = atoi(e); if (v >= 1) g.stages = -v; }
   g.row_blocks = (int)cdiv(g.M, bm);
   g.col_tiles = (int)cdiv(g.N, bn);
-  g.stages = mh == 2 ? pick_stages<2>(g.nk, smem_extra) : pick_stages<1>(g.nk, smem_extra);
+  { const int forced = g.stages < 0 ? -g.stages : 0;
+    g.stages = mh == 2 ? pick_stages<2>(g.nk, smem_extra) : pick_stages<1>(g.nk, smem_extra);
+    if (forced && forced < g.stages) g.stages = forced; }
   g.sched_mode = sched_mode;
   const long T = (long)g.row_blocks * g.col_tiles;
   const int sms = num_sms();
