@@ -218,7 +218,7 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
 // loop carries no per-element index bookkeeping.  Hardest POSITIVES are mined in bh_finalize from the per-label
 // chains (a handful of candidates per anchor).
 struct MineEpi {
-  static constexpr int SMEM_PER_WARP = 0;
+  static constexpr int SMEM_PER_WARP = 2 * 512;      // double-buffered {sq[64], labels[64]} of the warp's column slice
   static constexpr int CW = 16;
   struct Params {
     const float* sq;          // |x_j|^2 of the mining rows, (B_all)
@@ -238,16 +238,26 @@ struct MineEpi {
     s.nbest = INFINITY;
     s.ngrp = -1;
   }
+  // per-column data of the warp's 64-column slice -> shared memory, one tile ahead (16 B per lane, cp.async)
+  static __device__ __forceinline__ void prefetch(const Params& p, const tc::GramParams&, float* scratch, int buf, int colw) {
+    const int lane = threadIdx.x & 31;
+    float* dst = scratch + buf * 128 + lane * 4;                     // [0,64): sq, [64,128): labels (bit patterns)
+    const void* src = lane < 16 ? (const void*)(p.sq + colw + lane * 4) : (const void*)(p.labels + colw + (lane - 16) * 4);
+    tc::cp_async16(dst, src);
+    tc::cp_async_commit();
+  }
+  static __device__ __forceinline__ void prefetch_wait() { tc::cp_async_wait_all(); __syncwarp(); }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
-                                               const uint32_t (&acc)[16], int col0, float*) {
+                                               const uint32_t (&acc)[16], int col0, float* scratch, int bc) {
     // no edge handling: sq/labels are padded to whole tiles with |x|^2 = +inf and TMA zero-fills the Gram there
-    const float4* sq4 = reinterpret_cast<const float4*>(p.sq + col0);
-    const int4* lb4 = reinterpret_cast<const int4*>(p.labels + col0);
+    const float* tile = scratch + (bc >> 2) * 128;                   // this tile's {sq[64], labels[64]}
+    const float4* sq4 = reinterpret_cast<const float4*>(tile + (bc & 3) * 16);
+    const int4* lb4 = reinterpret_cast<const int4*>(tile + 64 + (bc & 3) * 16);
     float pm[4];                                     // group-of-4 minima
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 s4 = __ldg(sq4 + q);
-      const int4 l4 = __ldg(lb4 + q);
+      const float4 s4 = sq4[q];
+      const int4 l4 = lb4[q];
       const float v0 = fmaf(-2.f, __uint_as_float(acc[4 * q + 0]), (l4.x == s.lab_i) ? INFINITY : s4.x);
       const float v1 = fmaf(-2.f, __uint_as_float(acc[4 * q + 1]), (l4.y == s.lab_i) ? INFINITY : s4.y);
       const float v2 = fmaf(-2.f, __uint_as_float(acc[4 * q + 2]), (l4.z == s.lab_i) ? INFINITY : s4.z);

@@ -277,7 +277,7 @@ template <int KMAX> struct TopkEpi {
     s.tk.init();
   }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
-                                               const uint32_t (&acc)[16], int col0, float*) {
+                                               const uint32_t (&acc)[16], int col0, float*, int) {
     const int ncols = g.N - col0;
     float m = -INFINITY;
     if (ncols >= 16) {
@@ -309,6 +309,8 @@ template <int KMAX> struct TopkEpi {
       }
     }
   }
+  static __device__ __forceinline__ void prefetch(const Params&, const tc::GramParams&, float*, int, int) {}
+  static __device__ __forceinline__ void prefetch_wait() {}
   static __device__ __forceinline__ void row_end(const Params& p, const tc::GramParams& g, int row, int cs, State& s) {
     if (!s.valid) return;
     const int part = (int)(blockIdx.x % g.splits) * p.col_slices + cs;                          // (split, column slice)
@@ -338,7 +340,7 @@ struct StoreEpi {
     s.row0 = row - (int)(threadIdx.x & 31);                   // first row of this warp's 32-row slab
   }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
-                                               const uint32_t (&acc)[16], int col0, float* scratch) {
+                                               const uint32_t (&acc)[16], int col0, float* scratch, int) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
 #pragma unroll
@@ -357,6 +359,8 @@ struct StoreEpi {
       }
     }
   }
+  static __device__ __forceinline__ void prefetch(const Params&, const tc::GramParams&, float*, int, int) {}
+  static __device__ __forceinline__ void prefetch_wait() {}
   static __device__ __forceinline__ void row_end(const Params&, const tc::GramParams&, int, int, State&) {}
 };
 

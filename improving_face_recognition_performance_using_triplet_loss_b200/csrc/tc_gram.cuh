@@ -91,6 +91,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity))
     if (++spins > 20000u) mbar_timeout(bar, parity);               // >= ~2 s of hardware sleeps
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile(
@@ -220,7 +225,9 @@ template <int MH> inline int pick_stages(int nk, int extra) {
 //   static constexpr int SMEM_PER_WARP;   (bytes of scratch shared memory per epilogue warp, may be 0)
 //   static constexpr int CW;              (16 or 32: columns per TMEM load / chunk)
 //   static __device__ void chunk(const Params&, const GramParams&, State&, int row, const uint32_t (&acc)[CW], int col0,
-//                                float* scratch);
+//                                float* scratch /* the warp's scratch */, int bc /* (tile parity) * 4 + chunk ordinal */);
+//   static __device__ void prefetch(const Params&, const GramParams&, float* scratch, int buf, int colw);  (may be a no-op)
+//   static __device__ void prefetch_wait();
 //   static __device__ void row_end(const Params&, const GramParams&, int row, int part, State&);
 // row = anchor/query row index of this thread, col0 = first Gram column of the 32-column chunk held in
 // acc (fp32 bit patterns); part = this warp's column slice (0..3) for partial-result slots.
@@ -349,16 +356,20 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int part = cs;
     constexpr int CW = Epi::CW;                                      // columns per TMEM load / epilogue chunk
     int rb = rb0, ct = ct0;
+    if (ntiles > 0) Epi::prefetch(ep, g, scratch, 0, ct0 * BN + cs * COLS_PER_WARP);
     for (int i = 0; i < ntiles; ++i) {
       if (i == 0 || ct == 0) {
         if (i != 0) Epi::row_end(ep, g, row, part, st);
         row = rb * BM + rowhalf * 128 + quarter * 32 + lane;
         Epi::row_begin(ep, g, row, st);
       }
+      const int colw = ct * BN + cs * COLS_PER_WARP;                 // first column of this warp's slice
+      Epi::prefetch_wait();                                          // this tile's per-column data has landed
+      if (i + 1 < ntiles)                                            // next tile's data: in flight during this tile
+        Epi::prefetch(ep, g, scratch, (i + 1) & 1, (ct + 1 == CT ? 0 : ct + 1) * BN + cs * COLS_PER_WARP);
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + rowhalf * BN + cs * COLS_PER_WARP);
-      const int colw = ct * BN + cs * COLS_PER_WARP;                 // first column of this warp's slice
       if ((g.debug & 3) != 1) {
 #pragma unroll
         for (int c = 0; c < COLS_PER_WARP / CW; ++c) {
@@ -367,7 +378,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t v[CW];
             tmem_ld(t_acc + c * CW, v);
             tmem_ld_wait(v);
-            if ((g.debug & 3) != 2) Epi::chunk(ep, g, st, row, v, col0, scratch);
+            if ((g.debug & 3) != 2) Epi::chunk(ep, g, st, row, v, col0, scratch, (i & 1) * 4 + c);
           }
         }
       }
