@@ -591,7 +591,7 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
     tc::GramParams g{};
     g.M = (int)B_local; g.N = (int)B_all; g.nk = L.Dp / tc::BK;
     const int mh = tc::pick_mh(g.M, g.nk);
-    const int grid = tc::plan_gram(g, mh, 0);
+    const int grid = tc::plan_gram(g, mh, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS);
     MineEpi::Params ep{sq, lab, kneg, (int)row_offset};
     return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st);
   }
