@@ -55,8 +55,6 @@ def sharded_topk(local_scores: torch.Tensor, local_idx: torch.Tensor, group=None
     merge = _merge or merge_topk
     world = dist.get_world_size(group)
     nq, K = local_scores.shape
-    ps = torch.empty((world, nq, K), dtype=local_scores.dtype, device=local_scores.device)
-    pi = torch.empty((world, nq, K), dtype=local_idx.dtype, device=local_idx.device)
-    dist.all_gather_into_tensor(ps, local_scores.contiguous(), group=group)
-    dist.all_gather_into_tensor(pi, local_idx.contiguous(), group=group)
+    ps = all_gather_rows(local_scores, group).reshape(world, nq, K)     # rank-major concatenation along dim 0
+    pi = all_gather_rows(local_idx, group).reshape(world, nq, K)
     return merge(ps, pi)
