@@ -23,7 +23,7 @@ struct BhLayout {
   bool xm_f32;          // fp32 mining rows materialised in the workspace
   int Dp;               // K padded to a multiple of 64 (tensor-core path)
   int tbits;            // log2 of the label hash-table size
-  size_t kpos, kneg, sq, nrm, lab, xm, hkeys, hhead, rheadp, rheadn, hnext, hslot, rnextp, rnextn, wgt, clr_begin, clr_bytes, total;
+  size_t kpos, kneg, sq, nrm, lab, xm, hkeys, hcnt, hhead, rheadp, rheadn, hmem, hnext, hslot, rnextp, rnextn, wgt, clr_begin, clr_bytes, total;
 };
 
 BhLayout bh_layout(long B_local, long B_all, long D, int dtype, int flags) {
@@ -43,13 +43,15 @@ BhLayout bh_layout(long B_local, long B_all, long D, int dtype, int flags) {
   L.lab = take(Bpad * 4);
   L.xm = take(L.use_tc ? (size_t)B_all * L.Dp * 2 : (L.xm_f32 ? (size_t)B_all * D * 4 : 0));
   // per-label chains (tensor-core path): open-addressing table of (label -> head row), next pointers, slot per row
-  // one memset(0xFF) resets [hkeys | hhead | rheadp | rheadn]: empty label table, empty chains (-1 heads)
+  // one memset(0xFF) resets [hkeys | hcnt | hhead | rheadp | rheadn]: empty label table, empty chains (-1 heads)
   L.hkeys = take(L.use_tc ? (size_t)8 << L.tbits : 0);
-  L.hhead = take(L.use_tc ? (size_t)4 << L.tbits : 0);
+  L.hcnt = take(L.use_tc ? (size_t)4 << L.tbits : 0);        // members - 1 per label slot (starts at -1)
+  L.hhead = take(L.use_tc ? (size_t)4 << L.tbits : 0);       // overflow chain (members beyond the 8 inline ones)
   L.rheadp = take((size_t)B_all * 4);                        // rows that chose r as hardest positive (chain heads)
   L.rheadn = take((size_t)B_all * 4);                        // rows that chose r as hardest negative
   L.clr_begin = L.use_tc ? L.hkeys : L.rheadp;
   L.clr_bytes = off - L.clr_begin;
+  L.hmem = take(L.use_tc ? (size_t)32 << L.tbits : 0);       // first 8 member rows of every label slot, inline
   L.hnext = take(L.use_tc ? (size_t)B_all * 4 : 0);
   L.hslot = take(L.use_tc ? (size_t)B_all * 4 : 0);
   L.rnextp = take((size_t)B_local * 4);
@@ -81,8 +83,8 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
                float* __restrict__ nrm, int32_t* __restrict__ lab_ws, __nv_bfloat16* __restrict__ xm_bf16,
                float* __restrict__ xm_f32, unsigned long long* __restrict__ kpos,
                unsigned long long* __restrict__ kneg, float* __restrict__ dE,
-               unsigned long long* __restrict__ hkeys, int32_t* __restrict__ hhead, int32_t* __restrict__ hnext,
-               int32_t* __restrict__ hslot, int tbits) {
+               unsigned long long* __restrict__ hkeys, int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem,
+               int32_t* __restrict__ hhead, int32_t* __restrict__ hnext, int32_t* __restrict__ hslot, int tbits) {
   const long row = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= B_all) return;
   const int lane = threadIdx.x & 31;
@@ -195,7 +197,7 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
     }
     const long li = row - row_offset;
     if (kpos && li >= 0 && li < B_local) { kpos[li] = KEY_POS_EMPTY; kneg[li] = KEY_NEG_EMPTY; }
-    if (hkeys) {                                     // push this row on its label's chain
+    if (hkeys) {                                     // register this row with its label (open-addressing table)
       const unsigned long long tag = (unsigned long long)(uint32_t)lab;     // upper half 0: never equals EMPTY (~0)
       const uint32_t mask = (1u << tbits) - 1u;
       uint32_t sl = ((uint32_t)lab * 2654435761u) >> (32 - tbits);
@@ -205,7 +207,9 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
         sl = (sl + 1) & mask;
       }
       hslot[row] = (int32_t)sl;
-      hnext[row] = atomicExch(&hhead[sl], (int32_t)row);
+      const int pos = atomicAdd(&hcnt[sl], 1) + 1;                   // counter starts at -1
+      if (pos < 8) hmem[sl * 8 + pos] = (int32_t)row;                // inline member list: no pointer chasing later
+      else hnext[row] = atomicExch(&hhead[sl], (int32_t)row);        // overflow chain (labels with > 8 rows)
     }
   }
 }
@@ -385,6 +389,7 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
                    long row_offset, long B_local, float margin, const float* __restrict__ head_grad, int detach,
                    int mode, const unsigned long long* __restrict__ kpos, const unsigned long long* __restrict__ kneg,
                    const __nv_bfloat16* __restrict__ xm, int Dp, const int32_t* __restrict__ lab,
+                   const int32_t* __restrict__ hcnt, const int32_t* __restrict__ hmem,
                    const int32_t* __restrict__ hhead, const int32_t* __restrict__ hnext,
                    const int32_t* __restrict__ hslot, float* __restrict__ loss, int32_t* __restrict__ idx_p,
                    int32_t* __restrict__ idx_n, float* __restrict__ wgt, int32_t* __restrict__ rheadp,
@@ -399,22 +404,47 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     ip = (kp == KEY_POS_EMPTY) ? -1 : (int)(0xffffffffu - (uint32_t)(kp & 0xffffffffull));
     in = (kn == KEY_NEG_EMPTY) ? -1 : (int)(uint32_t)(kn & 0xffffffffull);
   } else if (mode == 1) {
+    // 16 candidate slots x 2 lanes: slots 0-7 = inline same-label members, slots 8-11 = the 4 columns of the
+    // negative group; every lane sums half a row, so all candidate distances cost one memory round trip.
     const __nv_bfloat16* xi = xm + gi * Dp;
-    float bd = -INFINITY;
-    for (int j = hhead[hslot[gi]]; j >= 0; j = hnext[j]) {          // same-label rows (chain order is arbitrary)
-      if (j == gi) continue;
-      const float d = xm_dist(xi, xm + (long)j * Dp, Dp, lane);
-      if (d > bd || (d == bd && j < ip) || ip < 0) { bd = d; ip = j; }
-    }
+    const int my = lab[gi];
+    const int sl = hslot[gi];
+    const int cnt = hcnt[sl] + 1;
     const unsigned long long kn = kneg[li];
-    if (kn != KEY_NEG_EMPTY) {
-      const int g0 = (int)(uint32_t)(kn & 0xffffffffull);
-      const int my = lab[gi];
-      float nd = INFINITY;
-      for (int c = g0; c < g0 + 4 && c < B_all; ++c) {               // ascending + strict '<': lowest index on ties
-        if (lab[c] == my) continue;
-        const float d = xm_dist(xi, xm + (long)c * Dp, Dp, lane);
-        if (d < nd || in < 0) { nd = d; in = c; }
+    const int g0 = (kn == KEY_NEG_EMPTY) ? -1 : (int)(uint32_t)(kn & 0xffffffffull);
+    const int slot = lane >> 1, half = lane & 1;
+    int cand = -1;
+    if (slot < 8) { if (slot < cnt) cand = hmem[sl * 8 + slot]; if (cand == gi) cand = -1; }
+    else if (slot < 12 && g0 >= 0) { const int c = g0 + slot - 8; if (c < B_all && lab[c] != my) cand = c; }
+    float d = 0.f;
+    if (cand >= 0) {
+      const __nv_bfloat16* xc = xm + (long)cand * Dp;
+      const int hb = half * (Dp / 2);
+      for (int e = hb; e < hb + Dp / 2; e += 8) {
+        float x[8], y[8];
+        load8<__nv_bfloat16>(xi + e, x);
+        load8<__nv_bfloat16>(xc + e, y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float t = x[k] - y[k]; d = fmaf(t, t, d); }
+      }
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    // hardest positive: max d over slots 0-7 (lowest index on ties); hardest negative: min d over slots 8-11
+    float pd = (slot < 8 && cand >= 0) ? d : -INFINITY; int pi = (slot < 8) ? cand : -1;
+    float nd = (slot >= 8 && cand >= 0) ? d : INFINITY; int ni = (slot >= 8) ? cand : -1;
+#pragma unroll
+    for (int o = 16; o > 1; o >>= 1) {
+      const float opd = __shfl_xor_sync(0xffffffffu, pd, o); const int opi = __shfl_xor_sync(0xffffffffu, pi, o);
+      if (opi >= 0 && (pi < 0 || opd > pd || (opd == pd && opi < pi))) { pd = opd; pi = opi; }
+      const float ond = __shfl_xor_sync(0xffffffffu, nd, o); const int oni = __shfl_xor_sync(0xffffffffu, ni, o);
+      if (oni >= 0 && (ni < 0 || ond < nd || (ond == nd && oni < ni))) { nd = ond; ni = oni; }
+    }
+    ip = pi; in = ni;
+    if (cnt > 8) {                                                   // rare: labels with more than 8 rows
+      for (int j = hhead[sl]; j >= 0; j = hnext[j]) {
+        if (j == gi) continue;
+        const float dj = xm_dist(xi, xm + (long)j * Dp, Dp, lane);
+        if (ip < 0 || dj > pd || (dj == pd && j < ip)) { pd = dj; ip = j; }
       }
     }
   } else {
@@ -647,6 +677,8 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   auto* xm_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + L.xm);
   float* xm_f32 = reinterpret_cast<float*>(ws + L.xm);
   auto* hkeys = L.use_tc ? reinterpret_cast<unsigned long long*>(ws + L.hkeys) : nullptr;
+  int32_t* hcnt = reinterpret_cast<int32_t*>(ws + L.hcnt);
+  int32_t* hmem = reinterpret_cast<int32_t*>(ws + L.hmem);
   int32_t* hhead = reinterpret_cast<int32_t*>(ws + L.hhead);
   int32_t* hnext = reinterpret_cast<int32_t*>(ws + L.hnext);
   int32_t* hslot = reinterpret_cast<int32_t*>(ws + L.hslot);
@@ -664,8 +696,8 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, labels_all, B_all, (int)D, L.Dp, normalize,
                                                           L.use_tc ? 1 : 0, L.xm_f32 ? 1 : 0, row_offset, B_local, sq, nrm,
-                                                          lab, xm_bf16, xm_f32, kpos, kneg, nullptr, hkeys, hhead, hnext,
-                                                          hslot, L.tbits);
+                                                          lab, xm_bf16, xm_f32, kpos, kneg, nullptr, hkeys, hcnt, hmem,
+                                                          hhead, hnext, hslot, L.tbits);
   });
   EFM_LAUNCH_CHECK("bh_prep");
   {
@@ -675,7 +707,7 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
                                                               B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos,
-                                                              kneg, xm_bf16, L.Dp, lab, hhead, hnext, hslot, loss, idx_p,
+                                                              kneg, xm_bf16, L.Dp, lab, hcnt, hmem, hhead, hnext, hslot, loss, idx_p,
                                                               idx_n, wgt, rheadp, rheadn, rnextp, rnextn);
   });
   EFM_LAUNCH_CHECK("bh_finalize");
@@ -732,14 +764,14 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nullptr, B_all, (int)D, (int)D, normalize, 0, 0, 0, 0,
                                                           sq, nrm, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                          nullptr, nullptr, nullptr, 0);
+                                                          nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   });
   EFM_LAUNCH_CHECK("bh_prep(stats)");
   if (B_local > 0) {
     EFM_BH_DISPATCH(dtype, vec, T, V, {
       bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
                                                                 B_local, margin, head_grad, detach, 2, nullptr, nullptr, nullptr,
-                                                                0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                 const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), wgt,
                                                                 rheadp, rheadn, rnextp, rnextn);
     });
