@@ -404,23 +404,33 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     ip = (kp == KEY_POS_EMPTY) ? -1 : (int)(0xffffffffu - (uint32_t)(kp & 0xffffffffull));
     in = (kn == KEY_NEG_EMPTY) ? -1 : (int)(uint32_t)(kn & 0xffffffffull);
   } else if (mode == 1) {
-    // 16 candidate slots x 2 lanes: slots 0-7 = inline same-label members, slots 8-11 = the 4 columns of the
-    // negative group; every lane sums half a row, so all candidate distances cost one memory round trip.
+    // Candidates: up to 7 inline same-label members (positives) + the 4 columns of the negative group.  They are
+    // compacted and spread over the warp (2/4/8/16 lanes each), so every lane sums an equal share of one candidate
+    // row and all distances cost one memory round trip.
     const __nv_bfloat16* xi = xm + gi * Dp;
     const int my = lab[gi];
     const int sl = hslot[gi];
     const int cnt = hcnt[sl] + 1;
     const unsigned long long kn = kneg[li];
     const int g0 = (kn == KEY_NEG_EMPTY) ? -1 : (int)(uint32_t)(kn & 0xffffffffull);
-    const int slot = lane >> 1, half = lane & 1;
-    int cand = -1;
-    if (slot < 8) { if (slot < cnt) cand = hmem[sl * 8 + slot]; if (cand == gi) cand = -1; }
-    else if (slot < 12 && g0 >= 0) { const int c = g0 + slot - 8; if (c < B_all && lab[c] != my) cand = c; }
+    int mine = -1;                                                   // lane l < 8: member l; lanes 8-11: group column
+    if (lane < 8) { if (lane < cnt) mine = hmem[sl * 8 + lane]; if (mine == gi) mine = -1; }
+    else if (lane < 12 && g0 >= 0) { const int c = g0 + lane - 8; if (c < B_all && lab[c] != my) mine = c; }
+    const unsigned vmask = __ballot_sync(0xffffffffu, mine >= 0);
+    const int ncand = __popc(vmask);
+    int lanes_per = ncand <= 2 ? 16 : (ncand <= 4 ? 8 : (ncand <= 8 ? 4 : 2));
+    while (lanes_per > 2 && Dp / lanes_per < 8) lanes_per >>= 1;     // at least one 8-element slab per lane
+    const int slot = lane / lanes_per, part = lane % lanes_per;
+    // source lane of the slot-th valid candidate
+    int src = -1;
+    { unsigned m = vmask; for (int k = 0; k < slot && m; ++k) m &= m - 1; if (m && slot < ncand) src = __ffs(m) - 1; }
+    const int cand = __shfl_sync(0xffffffffu, mine, src < 0 ? 0 : src);
+    const bool is_pos = src >= 0 && src < 8;
     float d = 0.f;
-    if (cand >= 0) {
+    if (src >= 0) {
       const __nv_bfloat16* xc = xm + (long)cand * Dp;
-      const int hb = half * (Dp / 2);
-      for (int e = hb; e < hb + Dp / 2; e += 8) {
+      const int span = Dp / lanes_per, e0 = part * span;
+      for (int e = e0; e < e0 + span; e += 8) {
         float x[8], y[8];
         load8<__nv_bfloat16>(xi + e, x);
         load8<__nv_bfloat16>(xc + e, y);
@@ -428,12 +438,13 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
         for (int k = 0; k < 8; ++k) { const float t = x[k] - y[k]; d = fmaf(t, t, d); }
       }
     }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    // hardest positive: max d over slots 0-7 (lowest index on ties); hardest negative: min d over slots 8-11
-    float pd = (slot < 8 && cand >= 0) ? d : -INFINITY; int pi = (slot < 8) ? cand : -1;
-    float nd = (slot >= 8 && cand >= 0) ? d : INFINITY; int ni = (slot >= 8) ? cand : -1;
 #pragma unroll
-    for (int o = 16; o > 1; o >>= 1) {
+    for (int o = 1; o < 16; o <<= 1) { const float od = __shfl_xor_sync(0xffffffffu, d, o); if (o < lanes_per) d += od; }
+    // hardest positive: max d (lowest index on ties); hardest negative: min d (lowest index on ties)
+    float pd = (src >= 0 && is_pos) ? d : -INFINITY; int pi = (src >= 0 && is_pos) ? cand : -1;
+    float nd = (src >= 0 && !is_pos) ? d : INFINITY; int ni = (src >= 0 && !is_pos) ? cand : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
       const float opd = __shfl_xor_sync(0xffffffffu, pd, o); const int opi = __shfl_xor_sync(0xffffffffu, pi, o);
       if (opi >= 0 && (pi < 0 || opd > pd || (opd == pd && opi < pi))) { pd = opd; pi = opi; }
       const float ond = __shfl_xor_sync(0xffffffffu, nd, o); const int oni = __shfl_xor_sync(0xffffffffu, ni, o);
@@ -456,7 +467,8 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     return;
   }
   const T* ea = E + gi * D; const T* epp = E + (long)ip * D; const T* en = E + (long)in * D;
-  const float na = normalize ? nrm[gi] : 1.f, np_ = normalize ? nrm[ip] : 1.f, nn = normalize ? nrm[in] : 1.f;
+  // x = e * (1/|e|): one reciprocal per row instead of a division per element (<= 1 ulp from e/|e|)
+  const float ra = normalize ? 1.f / nrm[gi] : 1.f, rp = normalize ? 1.f / nrm[ip] : 1.f, rn = normalize ? 1.f / nrm[in] : 1.f;
   float s = 0.f;
   if constexpr (VEC8) {
     for (int d = lane * 8; d < D; d += 256) {
@@ -464,17 +476,15 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
       load8<T>(ea + d, a); load8<T>(epp + d, p); load8<T>(en + d, n);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float av = a[k], pv = p[k], nv = n[k];
-        if (normalize) { av = av / na; pv = pv / np_; nv = nv / nn; }
-        const float dp = pv - av, dn = nv - av;
+        const float av = a[k] * ra;
+        const float dp = fmaf(p[k], rp, -av), dn = fmaf(n[k], rn, -av);
         s += dp * dp - dn * dn;
       }
     }
   } else {
     for (int d = lane; d < D; d += 32) {
-      float a = El<T>::to_f(ea[d]), p = El<T>::to_f(epp[d]), n = El<T>::to_f(en[d]);
-      if (normalize) { a = a / na; p = p / np_; n = n / nn; }
-      const float dp = p - a, dn = n - a;
+      const float a = El<T>::to_f(ea[d]) * ra;
+      const float dp = fmaf(El<T>::to_f(epp[d]), rp, -a), dn = fmaf(El<T>::to_f(en[d]), rn, -a);
       s += dp * dp - dn * dn;
     }
   }
@@ -501,18 +511,18 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
 // + sum_{j: n(j)=r} w_j (x_j - x_r), then (normalize) dE_r = (dX_r - x_r (x_r . dX_r)) / |e_r|.  Every output row is
 // written exactly once with plain stores: no zero-fill, no floating-point atomics, no separate normalise-backward pass.
 template <typename T, int VEC>
-__device__ __forceinline__ void load_slab(const T* p, int d, int D, float inv, float (&o)[VEC]) {
+__device__ __forceinline__ void load_slab(const T* p, int d, int D, float rinv, float (&o)[VEC]) {
   if constexpr (VEC == 8) {
     if (d < D) {
       load8<T>(p + d, o);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = o[k] / inv;
+      for (int k = 0; k < 8; ++k) o[k] = o[k] * rinv;
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = 0.f;
     }
   } else {
-    o[0] = d < D ? El<T>::to_f(p[d]) / inv : 0.f;
+    o[0] = d < D ? El<T>::to_f(p[d]) * rinv : 0.f;
   }
 }
 
@@ -526,7 +536,7 @@ bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int norma
   if (r >= B_all) return;
   const int lane = threadIdx.x & 31;
   const T* er = E + r * D;
-  const float nr = normalize ? nrm[r] : 1.f;
+  const float nr = normalize ? 1.f / nrm[r] : 1.f;              // reciprocal norm of this row
   const long li = r - row_offset;
   const bool anchor = li >= 0 && li < B_local;
   const float wa = anchor ? wgt[li] : 0.f;
@@ -543,15 +553,15 @@ bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int norma
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
     if (wa != 0.f) {
       float p[VEC], n[VEC];
-      load_slab<T, VEC>(E + (long)ap * D, d, D, normalize ? nrm[ap] : 1.f, p);
-      load_slab<T, VEC>(E + (long)an * D, d, D, normalize ? nrm[an] : 1.f, n);
+      load_slab<T, VEC>(E + (long)ap * D, d, D, normalize ? 1.f / nrm[ap] : 1.f, p);
+      load_slab<T, VEC>(E + (long)an * D, d, D, normalize ? 1.f / nrm[an] : 1.f, n);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = wa * (n[k] - p[k]);
     }
     for (int j = hp; j >= 0; j = rnextp[j]) {                        // r is the hardest positive of anchor j
       const long a = row_offset + j;
       float av[VEC];
-      load_slab<T, VEC>(E + a * D, d, D, normalize ? nrm[a] : 1.f, av);
+      load_slab<T, VEC>(E + a * D, d, D, normalize ? 1.f / nrm[a] : 1.f, av);
       const float w = wgt[j];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, x[k] - av[k], acc[k]);
@@ -559,7 +569,7 @@ bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int norma
     for (int j = hn; j >= 0; j = rnextn[j]) {                        // r is the hardest negative of anchor j
       const long a = row_offset + j;
       float av[VEC];
-      load_slab<T, VEC>(E + a * D, d, D, normalize ? nrm[a] : 1.f, av);
+      load_slab<T, VEC>(E + a * D, d, D, normalize ? 1.f / nrm[a] : 1.f, av);
       const float w = wgt[j];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, av[k] - x[k], acc[k]);
@@ -584,10 +594,10 @@ bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int norma
     if (d < D) {
       if constexpr (VEC == 8) {
         float4* o = reinterpret_cast<float4*>(dE + r * D + d);
-        o[0] = make_float4((acc[0] - x[0] * dot) / nr, (acc[1] - x[1] * dot) / nr, (acc[2] - x[2] * dot) / nr, (acc[3] - x[3] * dot) / nr);
-        o[1] = make_float4((acc[4] - x[4] * dot) / nr, (acc[5] - x[5] * dot) / nr, (acc[6] - x[6] * dot) / nr, (acc[7] - x[7] * dot) / nr);
+        o[0] = make_float4((acc[0] - x[0] * dot) * nr, (acc[1] - x[1] * dot) * nr, (acc[2] - x[2] * dot) * nr, (acc[3] - x[3] * dot) * nr);
+        o[1] = make_float4((acc[4] - x[4] * dot) * nr, (acc[5] - x[5] * dot) * nr, (acc[6] - x[6] * dot) * nr, (acc[7] - x[7] * dot) * nr);
       } else {
-        dE[r * D + d] = (acc[0] - x[0] * dot) / nr;
+        dE[r * D + d] = (acc[0] - x[0] * dot) * nr;
       }
     }
     return;
@@ -599,7 +609,7 @@ bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int norma
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       float* o = dE + r * D + d + k;
-      *o = (*o - x[k] * dot) / nr;
+      *o = (*o - x[k] * dot) * nr;
     }
   }
 }
