@@ -384,7 +384,7 @@ __device__ __forceinline__ float xm_dist(const __nv_bfloat16* a, const __nv_bflo
 // hardest positive from the anchor's label chain, hardest negative = best non-same-label column inside the
 // group of 4 the Gram kernel selected; both by exact fp32 distances on the bf16 mining rows.  mode 2: indices given.
 template <typename T, bool VEC8>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 6)
 bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int normalize, long B_all, int D,
                    long row_offset, long B_local, float margin, const float* __restrict__ head_grad, int detach,
                    int mode, const unsigned long long* __restrict__ kpos, const unsigned long long* __restrict__ kneg,
@@ -429,8 +429,8 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     float d = 0.f;
     if (src >= 0) {
       const __nv_bfloat16* xc = xm + (long)cand * Dp;
-      const int span = Dp / lanes_per, e0 = part * span;
-      for (int e = e0; e < e0 + span; e += 8) {
+      // the lanes of one candidate read adjacent 16-byte pieces: every 32-byte sector is requested once
+      for (int e = part * 8; e < Dp; e += lanes_per * 8) {
         float x[8], y[8];
         load8<__nv_bfloat16>(xi + e, x);
         load8<__nv_bfloat16>(xc + e, y);
@@ -527,7 +527,7 @@ __device__ __forceinline__ void load_slab(const T* p, int d, int D, float rinv, 
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 6)
 bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int normalize, long B_all, int D,
                long row_offset, long B_local, const int32_t* __restrict__ idx_p, const int32_t* __restrict__ idx_n,
                const float* __restrict__ wgt, const int32_t* __restrict__ rheadp, const int32_t* __restrict__ rheadn,
