@@ -186,38 +186,63 @@ topk_select_kernel(const float* __restrict__ scores, long N, int K, float sim_th
   }
 }
 
-// K-way merge: one warp per query; K rounds of "best candidate strictly worse than the previous pick".
+// K-way merge of `parts` partial lists per query: one block per query.  Every thread folds a strided share of the
+// parts*K candidates into a sorted register list, then warp 0 pops the K best of the 256 lists from shared memory.
+template <int KMAX>
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ part_s, const int32_t* __restrict__ part_i, int parts, long nq, int K,
-                  int KS /*stride of a partial list*/, float* __restrict__ out_s, int32_t* __restrict__ out_i) {
-  const long q = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (q >= nq) return;
-  const int lane = threadIdx.x & 31;
-  float ps = INFINITY; int pi = -1;                         // previous pick (better than everything)
-  bool first = true;
-  for (int k = 0; k < K; ++k) {
-    float bs = -INFINITY; int bi = -1;
-    for (int c = lane; c < parts * K; c += 32) {
-      const int p = c / K, kk = c % K;
-      const long o = ((long)p * nq + q) * KS + kk;
-      const int i = part_i[o];
-      if (i < 0) continue;
-      const float s = part_s[o];
-      const bool after_prev = first || (s < ps) || (s == ps && i > pi);
-      if (after_prev && TopK<1>::better(s, i, bs, bi)) { bs = s; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi >= 0 && TopK<1>::better(os, oi, bs, bi)) { bs = os; bi = oi; }
-    }
-    if (lane == 0) { out_s[q * K + k] = bi >= 0 ? bs : 0.f; out_i[q * K + k] = bi; }
-    if (bi < 0) {                                            // exhausted: fill the rest
-      for (int r = k + 1 + lane; r < K; r += 32) { out_s[q * K + r] = 0.f; out_i[q * K + r] = -1; }
-      break;
-    }
-    ps = bs; pi = bi; first = false;
+                  float* __restrict__ out_s, int32_t* __restrict__ out_i) {
+  __shared__ float ls[256 * KMAX];
+  __shared__ int li[256 * KMAX];
+  const long q = blockIdx.x;
+  TopK<KMAX> tk;
+  tk.init();
+  const int total = parts * K;
+  for (int c = threadIdx.x; c < total; c += 256) {
+    const int p = c / K, kk = c % K;
+    const long o = ((long)p * nq + q) * K + kk;
+    const int i = part_i[o];
+    if (i >= 0) tk.insert(part_s[o], i);
   }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) { ls[threadIdx.x * KMAX + k] = tk.s[k]; li[threadIdx.x * KMAX + k] = tk.id[k]; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int head[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) head[j] = 0;
+    for (int k = 0; k < K; ++k) {
+      float bs = -INFINITY; int bi = -1, bj = -1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int t = threadIdx.x * 8 + j;
+        if (head[j] < KMAX) {
+          const float s = ls[t * KMAX + head[j]]; const int i = li[t * KMAX + head[j]];
+          if (i >= 0 && TopK<KMAX>::better(s, i, bs, bi)) { bs = s; bi = i; bj = j; }
+        }
+      }
+      float ws = bs; int wi = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, ws, o); const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (oi >= 0 && TopK<KMAX>::better(os, oi, ws, wi)) { ws = os; wi = oi; }
+      }
+      if (wi >= 0 && wi == bi) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j == bj) head[j]++;
+      }
+      if (threadIdx.x == 0) { out_s[q * K + k] = wi >= 0 ? ws : 0.f; out_i[q * K + k] = wi; }
+    }
+  }
+}
+
+static int launch_topk_merge(const float* ps, const int32_t* pi, int parts, long nq, int K, float* out_s, int32_t* out_i,
+                             cudaStream_t st) {
+  if (K == 1) topk_merge_kernel<1><<<(unsigned)nq, 256, 0, st>>>(ps, pi, parts, nq, K, out_s, out_i);
+  else if (K <= 5) topk_merge_kernel<5><<<(unsigned)nq, 256, 0, st>>>(ps, pi, parts, nq, K, out_s, out_i);
+  else topk_merge_kernel<EFM_GAL_MAX_K><<<(unsigned)nq, 256, 0, st>>>(ps, pi, parts, nq, K, out_s, out_i);
+  EFM_LAUNCH_CHECK("topk_merge");
+  return EFM_OK;
 }
 
 // ------------------------------------------------------------------------------------------ operand prep for the tcgen05 paths
@@ -279,34 +304,48 @@ template <int KMAX> struct TopkEpi {
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
                                                const uint32_t (&acc)[16], int col0, float*, int) {
     const int ncols = g.N - col0;
-    float m = -INFINITY;
+    float est[16];                                   // g * (1/gnorm): cheap estimate of sim * |q|
     if (ncols >= 16) {
       const float4* r4 = reinterpret_cast<const float4*>(p.rgn + col0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 r = __ldg(r4 + q);
-        m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(acc[4 * q]) * r.x, __uint_as_float(acc[4 * q + 1]) * r.y),
-                           fmaxf(__uint_as_float(acc[4 * q + 2]) * r.z, __uint_as_float(acc[4 * q + 3]) * r.w)));
+        est[4 * q + 0] = __uint_as_float(acc[4 * q + 0]) * r.x;
+        est[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) * r.y;
+        est[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) * r.z;
+        est[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) * r.w;
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (k < ncols) m = fmaxf(m, __uint_as_float(acc[k]) * p.rgn[col0 + k]);
+      for (int k = 0; k < 16; ++k) est[k] = (k < ncols) ? __uint_as_float(acc[k]) * p.rgn[col0 + k] : -INFINITY;
     }
-    // conservative filter: can the chunk maximum enter the list?
+    float m = est[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) m = fmaxf(m, est[k]);
+    // conservative filter: can the chunk maximum enter the list?  (reciprocal-multiply estimate, 1e-5 slack)
     float cut = p.sim_th;
     if (s.tk.full()) cut = fmaxf(cut, s.tk.s[KMAX - 1]);
-    const float cand = m * s.rqn;
-    if (!(cand >= cut - fabsf(cut) * 1e-5f - 1e-30f) && !(cand != cand)) return;
-#pragma unroll 1
-    for (int k = 0; k < 16; ++k) {
-      if (k < ncols) {
-        float a = __uint_as_float(acc[0]);
+    const float cutm = (cut - fabsf(cut) * 1e-5f - 1e-30f) * s.qn;   // compare g / gnorm against cut * |q|
+    bool anynan = false;
 #pragma unroll
-        for (int t = 1; t < 16; ++t) a = (t == k) ? __uint_as_float(acc[t]) : a;
-        const float sim = __fdiv_rn(a, __fmul_rn(p.gnorm[col0 + k], s.qn));
-        if (accept_score(sim, p.sim_th, p.flags)) s.tk.insert(sim, col0 + k);
-      }
+    for (int k = 0; k < 16; ++k) anynan |= (est[k] != est[k]);
+    if (!(m >= cutm) && !anynan) return;
+    // rare: collect the surviving elements in a bit mask, then evaluate exactly (IEEE division) only those.
+    // One copy of the insertion code, accumulators re-read from a local-memory copy by dynamic index (the fully
+    // unrolled form made the kernel instruction-cache bound: 55 % stall_no_inst in ncu).
+    unsigned mask = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) mask |= ((est[k] >= cutm || est[k] != est[k]) ? 1u : 0u) << k;
+    float tmp[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tmp[k] = __uint_as_float(acc[k]);
+#pragma unroll 1
+    while (mask) {
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (k >= ncols) break;
+      const float sim = __fdiv_rn(tmp[k], __fmul_rn(p.gnorm[col0 + k], s.qn));
+      if (accept_score(sim, p.sim_th, p.flags)) s.tk.insert(sim, col0 + k);
     }
   }
   static __device__ __forceinline__ void prefetch(const Params&, const tc::GramParams&, float*, int, int) {}
@@ -488,9 +527,7 @@ extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long 
       else topk_select_kernel<EFM_GAL_MAX_K><<<grid, 256, 0, st>>>(sc, N, K, sim_th, flags, idx_base, ps + qs * K, pi + qs * K, nq);
       EFM_LAUNCH_CHECK("topk_select");
     }
-    topk_merge_kernel<<<(unsigned)cdiv(nq, 8), 256, 0, st>>>(ps, pi, chunks, nq, K, K, out_score, out_idx);
-    EFM_LAUNCH_CHECK("topk_merge");
-    return EFM_OK;
+    return launch_topk_merge(ps, pi, chunks, nq, K, out_score, out_idx, st);
   }
 
   EFM_REQUIRE(dtype == EFM_BF16 || dtype == EFM_F16, EFM_E_ARG, "efm_gallery_topk: dtype %d", dtype);
@@ -526,17 +563,15 @@ extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long 
   if (K == 1) {
     TopkEpi<1>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
     rc = topk_tc_launch<1>(Gop, qpad, mh, g, grid, ep, st);
-  } else if (K <= 8) {
-    TopkEpi<8>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
-    rc = topk_tc_launch<8>(Gop, qpad, mh, g, grid, ep, st);
+  } else if (K <= 5) {
+    TopkEpi<5>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
+    rc = topk_tc_launch<5>(Gop, qpad, mh, g, grid, ep, st);
   } else {
     TopkEpi<EFM_GAL_MAX_K>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
     rc = topk_tc_launch<EFM_GAL_MAX_K>(Gop, qpad, mh, g, grid, ep, st);
   }
   if (rc) return rc;
-  topk_merge_kernel<<<(unsigned)cdiv(nq, 8), 256, 0, st>>>(ps, pi, parts, nq, K, K, out_score, out_idx);
-  EFM_LAUNCH_CHECK("topk_merge");
-  return EFM_OK;
+  return launch_topk_merge(ps, pi, parts, nq, K, out_score, out_idx, st);
 }
 
 extern "C" int efm_topk_merge(const float* part_score, const int32_t* part_idx, int parts, long nq, int K,
@@ -544,10 +579,8 @@ extern "C" int efm_topk_merge(const float* part_score, const int32_t* part_idx, 
   EFM_REQUIRE(parts >= 1 && nq >= 0 && K >= 1, EFM_E_ARG, "efm_topk_merge: bad arguments parts=%d nq=%ld K=%d", parts, nq, K);
   if (nq == 0) return EFM_OK;
   EFM_REQUIRE(part_score && part_idx && out_score && out_idx, EFM_E_ARG, "efm_topk_merge: null pointer");
-  topk_merge_kernel<<<(unsigned)cdiv(nq, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(part_score, part_idx, parts, nq,
-                                                                                          K, K, out_score, out_idx);
-  EFM_LAUNCH_CHECK("topk_merge");
-  return EFM_OK;
+  EFM_REQUIRE(K <= EFM_GAL_MAX_K && nq < (1L << 31), EFM_E_ARG, "efm_topk_merge: K <= %d", EFM_GAL_MAX_K);
+  return launch_topk_merge(part_score, part_idx, parts, nq, K, out_score, out_idx, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------ all-pairs cosine

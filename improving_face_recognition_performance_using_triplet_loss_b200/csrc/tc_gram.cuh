@@ -447,7 +447,7 @@ inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0) 
     return (int)(T < sms ? T : sms);
   }
   // mode 1: every row block is cut into `splits` column ranges so that the grid covers the SMs
-  int splits = (int)cdiv(2L * sms, g.row_blocks);                    // ~2 CTAs per SM over the run
+  int splits = (int)cdiv((long)sms, g.row_blocks);                   // one wave of CTAs: fixed cost per CTA is ~8 us
   if (splits > g.col_tiles) splits = g.col_tiles;
   if (splits < 1) splits = 1;
   g.splits = splits;
