@@ -303,6 +303,7 @@ template <int KMAX> struct TopkEpi {
   }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
                                                const uint32_t (&acc)[16], int col0, float*, int) {
+    if (!s.valid) return;                            // padding rows of the last query block (their Gram is all zeros)
     const int ncols = g.N - col0;
     float est[16];                                   // g * (1/gnorm): cheap estimate of sim * |q|
     if (ncols >= 16) {

@@ -17,7 +17,7 @@ import numpy as np
 
 __all__ = [
     "bf16_round", "triplet_loss_fwd", "triplet_loss_bwd", "sample_negatives",
-    "pairwise_sqdist", "batch_hard_mine", "batch_hard_triplet", "batch_hard_triplet_fast",
+    "pairwise_sqdist", "batch_hard_mine", "batch_hard_triplet", "batch_hard_triplet_fast", "batch_hard_strip_fast",
     "norm", "l2norm_fwd", "l2norm_bwd", "frob_fwd", "frob_bwd",
     "mx_maximum", "mx_minimum", "efm3_fwd", "efm3_bwd", "mfm2_fwd", "mfm2_bwd",
     "cosine_pairs", "cosine_dist_literal", "cosine_allpairs", "format_cosine_csv",
@@ -216,6 +216,38 @@ def batch_hard_triplet_fast(E, labels, margin, normalize=True):
         dE = (dX - X * (X * dX).sum(axis=1, keepdims=True)) / nrm
     else:
         dE = dX
+    return loss, np.where(valid, idx_p, -1), np.where(valid, idx_n, -1), dE
+
+
+def batch_hard_strip_fast(E_all, labels_all, row_offset, num_local, margin, normalize=True):
+    """fp32 port for `num_local` anchors [row_offset, row_offset+num_local) mined against the whole (gathered) batch:
+    the per-rank work of global batch-hard mining.  Returns (loss, idx_p, idx_n, dE_all)."""
+    E_all = np.ascontiguousarray(E_all, dtype=F32)
+    y = np.asarray(labels_all).reshape(-1)
+    if normalize:
+        nrm = np.sqrt((E_all * E_all).sum(axis=1, keepdims=True))
+        X = E_all / nrm
+    else:
+        X = E_all
+    sl = slice(row_offset, row_offset + num_local)
+    Xa = X[sl]
+    sq = (X * X).sum(axis=1)
+    d = sq[sl, None] + sq[None, :] - F32(2) * (Xa @ X.T)
+    same = y[sl, None] == y[None, :]
+    rows = np.arange(num_local)
+    dp = np.where(same, d, -np.inf); dp[rows, rows + row_offset] = -np.inf
+    dn = np.where(same, np.inf, d)
+    idx_p = dp.argmax(axis=1); idx_n = dn.argmin(axis=1)
+    valid = np.isfinite(dp[rows, idx_p]) & np.isfinite(dn[rows, idx_n])
+    P = X[idx_p]; Nn = X[idx_n]
+    s = (np.square(P - Xa) - np.square(Nn - Xa)).sum(axis=1) + F32(margin)
+    loss = np.where(valid, np.maximum(s, 0), 0).astype(F32)
+    w = (loss > 0).astype(F32)[:, None]
+    dX = np.zeros_like(X)
+    dX[sl] += F32(2) * (Nn - P) * w
+    np.add.at(dX, idx_p, F32(2) * (P - Xa) * w)
+    np.add.at(dX, idx_n, F32(2) * (Xa - Nn) * w)
+    dE = (dX - X * (X * dX).sum(axis=1, keepdims=True)) / nrm if normalize else dX
     return loss, np.where(valid, idx_p, -1), np.where(valid, idx_n, -1), dE
 
 
