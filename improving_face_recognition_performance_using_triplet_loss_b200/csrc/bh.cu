@@ -631,9 +631,10 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
     tc::GramParams g{};
     g.M = (int)B_local; g.N = (int)B_all; g.nk = L.Dp / tc::BK;
     const int mh = tc::pick_mh(g.M, g.nk);
-    const int grid = tc::plan_gram(g, mh, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS);
+    const int cg = tc::pick_cg(g.M, mh, 0);
+    const int grid = tc::plan_gram(g, mh, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, cg);
     MineEpi::Params ep{sq, lab, kneg, (int)row_offset};
-    return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st);
+    return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st, cg);
   }
   const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
   const int row_blocks = (int)cdiv(B_local, FM);

@@ -40,7 +40,7 @@ constexpr int COLS_PER_WARP = 64;          // BN / (EPI_SLICES / MH) for both sh
 constexpr int PRODUCER_WARP = EPI_WARPS;
 constexpr int MMA_WARP = EPI_WARPS + 1;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_NK = 8;                 // K <= 512
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;        // 227 KB opt-in maximum per CTA
@@ -91,6 +91,50 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity))
     if (++spins > 20000u) mbar_timeout(bar, parity);               // >= ~2 s of hardware sleeps
 }
+// ---- 2-CTA (cta_group::2) helpers: the pair shares every B stage; CTA rank 0 issues the MMAs ---------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -140,6 +184,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) { return SMEM_DESC_
 
 // instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N given
 __host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(128 >> 4) << 24); }
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) { return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24); }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -198,10 +243,11 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 // ---- tile schedule -------------------------------------------------------------------------------------
+template <int CG>
 __device__ __forceinline__ void tile_range(const GramParams& g, long& t0, long& t1) {
   const long CT = g.col_tiles;
   if (g.sched_mode == 0) {
-    const long T = (long)g.row_blocks * CT, G = gridDim.x, c = blockIdx.x;
+    const long T = (long)g.row_blocks * CT, G = gridDim.x / CG, c = blockIdx.x / CG;   // CG = 2: one range per CTA pair
     t0 = c * T / G;
     t1 = (c + 1) * T / G;
   } else {
@@ -231,14 +277,22 @@ template <int MH> inline int pick_stages(int nk, int extra) {
 //   static __device__ void row_end(const Params&, const GramParams&, int row, int part, State&);
 // row = anchor/query row index of this thread, col0 = first Gram column of the 32-column chunk held in
 // acc (fp32 bit patterns); part = this warp's column slice (0..3) for partial-result slots.
-template <class Epi, int MH>
+// CG = 2 (requires MH = 1): two CTAs of a cluster form a 256 x 256 tile.  Each CTA keeps its own 128 A rows resident and
+// loads HALF of every B stage (128 of the 256 Gram columns, 16 KB); CTA rank 0 issues tcgen05.mma.cta_group::2 (M = 256)
+// which reads both halves, so every SM pulls half the B bytes from L2 and reads half the B bytes from shared memory per
+// MAC.  Barriers: full / a_full / acc_empty live in the leader (TMA of both CTAs credits the leader, the peer's epilogue
+// arrives remotely); empty / a_empty / acc_full are signalled in both CTAs by multicast tcgen05.commit.
+template <class Epi, int MH, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams g,
             const typename Epi::Params ep) {
-  constexpr int BM = Shape<MH>::BM, BN = Shape<MH>::BN;
-  constexpr int A_KB_BYTES = Shape<MH>::A_KB_BYTES, B_ST_BYTES = Shape<MH>::B_ST_BYTES;
+  static_assert(CG == 1 || MH == 1, "the 2-CTA path uses the 128 x 256 per-CTA shape");
+  constexpr int BM = Shape<MH>::BM, BN = Shape<MH>::BN;              // per-CTA accumulator tile
+  constexpr int A_KB_BYTES = Shape<MH>::A_KB_BYTES, B_ST_BYTES = Shape<MH>::B_ST_BYTES / CG;   // CG = 2: half a B stage per CTA
+  constexpr int B_ROWS = BN / CG;                                    // Gram columns this CTA loads per stage
   constexpr int ACC_COLS = 256;                                      // TMEM columns per accumulator buffer (MH * BN)
-  constexpr uint32_t IDESC = idesc_bf16_m128(BN);
+  constexpr uint32_t IDESC = CG == 2 ? idesc_bf16(256, BN) : idesc_bf16_m128(BN);
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;           // 0 = leader
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t sA = base;
@@ -264,18 +318,21 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_a_full, 1);
     mbar_init(bar_a_empty, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + 8 * a, 1); mbar_init(bar_acc_empty + 8 * a, EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + 8 * a, 1); mbar_init(bar_acc_empty + 8 * a, EPI_WARPS * CG); }
     fence_barrier_init();
   }
   if (warp == PRODUCER_WARP && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
-  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (warp == MMA_WARP) {
+    if constexpr (CG == 2) { tmem_alloc_2cta(tmem_slot, TMEM_COLS); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers + TMEM of both CTAs are live past this point
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   long t0l, t1l;
-  tile_range(g, t0l, t1l);
+  tile_range<CG>(g, t0l, t1l);
   const int CT = g.col_tiles;
   const int ntiles = (int)(t1l - t0l);
   const int rb0 = (int)(t0l / CT), ct0 = (int)(t0l % CT);           // the only divisions; tiles advance incrementally
@@ -289,14 +346,23 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (i == 0 || ct == 0) {                                       // new row block: (re)load the resident A block
         if (i != 0) { mbar_wait(bar_a_empty, a_empty_phase); a_empty_phase ^= 1; }
         if (leader) {
-          mbar_expect_tx(bar_a_full, (uint32_t)g.nk * A_KB_BYTES);
-          for (int kb = 0; kb < g.nk; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, bar_a_full, kb * BK, rb * BM);
+          if constexpr (CG == 2) {
+            if (crank == 0) mbar_expect_tx(bar_a_full, (uint32_t)g.nk * A_KB_BYTES * 2);      // both CTAs' A blocks
+            for (int kb = 0; kb < g.nk; ++kb)
+              tma_load_2d_2cta(sA + kb * A_KB_BYTES, &tmA, bar_a_full, kb * BK, (rb * 2 + (int)crank) * BM);
+          } else {
+            mbar_expect_tx(bar_a_full, (uint32_t)g.nk * A_KB_BYTES);
+            for (int kb = 0; kb < g.nk; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, bar_a_full, kb * BK, rb * BM);
+          }
         }
       }
       for (int kb = 0; kb < g.nk; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (leader) {
-          if (g.debug & 4) { mbar_arrive(bar_full + 8 * stage); }    // profiling: no B traffic
+          if constexpr (CG == 2) {                                  // this CTA's half of the B stage -> leader's barrier
+            if (crank == 0) mbar_expect_tx(bar_full + 8 * stage, B_ST_BYTES * 2);
+            tma_load_2d_2cta(sB + stage * B_ST_BYTES, &tmB, bar_full + 8 * stage, kb * BK, ct * BN + (int)crank * B_ROWS);
+          } else if (g.debug & 4) { mbar_arrive(bar_full + 8 * stage); }    // profiling: no B traffic
           else {
             mbar_expect_tx(bar_full + 8 * stage, B_ST_BYTES);
             tma_load_2d(sB + stage * B_ST_BYTES, &tmB, bar_full + 8 * stage, kb * BK, ct * BN);
@@ -306,7 +372,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (++ct == CT) { ct = 0; ++rb; }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == MMA_WARP && crank == 0) {
     const uint32_t leader = elect_one();
     int stage = 0; uint32_t phase = 0, a_full_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -327,24 +393,34 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-              for (int h = 0; h < MH; ++h)                           // row half h: A rows [128h, +128) -> TMEM columns [h*BN, +BN)
-                umma_bf16(d_tmem + h * BN, da + (uint64_t)((h * (128 * BK * 2) + k * 32) >> 4), db + (uint64_t)((k * 32) >> 4),
-                          IDESC, (kb | k) ? 1u : 0u);
+              for (int h = 0; h < MH; ++h) {                         // row half h: A rows [128h, +128) -> TMEM columns [h*BN, +BN)
+                if constexpr (CG == 2)
+                  umma_bf16_2cta(d_tmem, da + (uint64_t)((k * 32) >> 4), db + (uint64_t)((k * 32) >> 4), IDESC, (kb | k) ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem + h * BN, da + (uint64_t)((h * (128 * BK * 2) + k * 32) >> 4), db + (uint64_t)((k * 32) >> 4),
+                            IDESC, (kb | k) ? 1u : 0u);
+              }
             }
           }
-          umma_commit(bar_empty + 8 * stage);                        // stage reusable once these MMAs retire
+          if constexpr (CG == 2) umma_commit_2cta(bar_empty + 8 * stage);
+          else umma_commit(bar_empty + 8 * stage);                   // stage reusable once these MMAs retire
         }
         if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
       const bool last_of_rb = (i + 1 == ntiles) || (ct + 1 == CT);
       if (leader) {
-        umma_commit(bar_acc_full + 8 * acc);                         // accumulator ready for the epilogue
-        if (last_of_rb) umma_commit(bar_a_empty);                    // A row-block may be overwritten
+        if constexpr (CG == 2) {
+          umma_commit_2cta(bar_acc_full + 8 * acc);
+          if (last_of_rb) umma_commit_2cta(bar_a_empty);
+        } else {
+          umma_commit(bar_acc_full + 8 * acc);                       // accumulator ready for the epilogue
+          if (last_of_rb) umma_commit(bar_a_empty);                  // A row-block may be overwritten
+        }
       }
       if (++ct == CT) ct = 0;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp < EPI_WARPS) {
     // ---------------- epilogue warps ----------------
     constexpr int COL_SLICES = EPI_SLICES / MH;                      // column slices of 64 per row half
     const int quarter = warp & 3, slice = warp >> 2;
@@ -360,7 +436,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int i = 0; i < ntiles; ++i) {
       if (i == 0 || ct == 0) {
         if (i != 0) Epi::row_end(ep, g, row, part, st);
-        row = rb * BM + rowhalf * 128 + quarter * 32 + lane;
+        row = (rb * CG + (int)crank) * BM + rowhalf * 128 + quarter * 32 + lane;
         Epi::row_begin(ep, g, row, st);
       }
       const int colw = ct * BN + cs * COLS_PER_WARP;                 // first column of this warp's slice
@@ -384,7 +460,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(bar_acc_empty + 8 * acc, 0);   // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(bar_acc_empty + 8 * acc);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (++ct == CT) { ct = 0; ++rb; }
     }
@@ -392,29 +471,44 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody may still touch the peer's smem / TMEM
   tc_fence_after();
-  if (warp == MMA_WARP) { __syncwarp(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (warp == MMA_WARP) {
+    __syncwarp();
+    if constexpr (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ---- host side: tensor maps + launch ----------------------------------------------------------------------
 // 2-D bf16 row-major (rows, Kp) tensor map with a (64 x box_rows) box, SWIZZLE_128B, zero OOB fill.
 int make_tmap_bf16(CUtensorMap* out, const void* base, long rows, long Kp, int box_rows);
 
-template <class Epi, int MH>
+template <class Epi, int MH, int CG>
 int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Epi::Params& ep, int grid, cudaStream_t st) {
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, Shape<MH>::BM);
+  int rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, 128);       // A box: 128 rows per TMA (MH = 2 issues it per 256-row block)
+  if (MH == 2) rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, Shape<MH>::BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tmB, B, g.N, (long)g.nk * BK, Shape<MH>::BN);
+  rc = make_tmap_bf16(&tmB, B, g.N, (long)g.nk * BK, Shape<MH>::BN / CG);
   if (rc) return rc;
-  const size_t smem = smem_bytes<MH>(g.nk, g.stages, Epi::SMEM_PER_WARP * EPI_WARPS);
+  const size_t smem = 1024 + (size_t)g.nk * Shape<MH>::A_KB_BYTES + (size_t)g.stages * (Shape<MH>::B_ST_BYTES / CG) + 256 +
+                      Epi::SMEM_PER_WARP * EPI_WARPS;
   static bool attr_done = false;                                     // per instantiation
   if (!attr_done) {
-    EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi, MH, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
-  gram_kernel<Epi, MH><<<grid, THREADS, smem, st>>>(tmA, tmB, g, ep);
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EFM_CUDA(cudaLaunchKernelEx(&cfg, gram_kernel<Epi, MH, CG>, tmA, tmB, g, ep));
+  } else {
+    gram_kernel<Epi, MH, CG><<<grid, THREADS, smem, st>>>(tmA, tmB, g, ep);
+  }
   EFM_LAUNCH_CHECK("gram_kernel");
   return EFM_OK;
 }
@@ -428,9 +522,16 @@ inline int pick_mh(int M, int nk) {
   return 1;
 }
 
+// 2-CTA pairs (cta_group::2): sched_mode 0 only, K-resident A, at least one full pair of row blocks
+inline int pick_cg(int M, int mh, int sched_mode) {
+  if (mh != 1 || sched_mode != 0 || M <= 128) return 1;
+  if (const char* e = getenv("EFM_GRAM_CG")) { const int v = atoi(e); if (v == 1 || v == 2) return v; }
+  return 2;
+}
+
 // fills row_blocks / col_tiles / stages / schedule and returns the grid size
-inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0) {
-  const int bm = 128 * mh, bn = 256 / mh;
+inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0, int cg = 1) {
+  const int bm = 128 * mh * cg, bn = 256 / mh;
   { const char* e = getenv("EFM_GRAM_DEBUG"); g.debug = e ? atoi(e) : 0; }
   g.stages = 0;
   if (const char* e = getenv("EFM_GRAM_STAGES")) { const int v = atoi(e); if (v >= 1) g.stages = -v; }
@@ -438,12 +539,17 @@ inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0) 
   g.col_tiles = (int)cdiv(g.N, bn);
   { const int forced = g.stages < 0 ? -g.stages : 0;
     g.stages = mh == 2 ? pick_stages<2>(g.nk, smem_extra) : pick_stages<1>(g.nk, smem_extra);
+    if (cg == 2) {                                                   // half-size stages: twice as many fit
+      g.stages = (int)((SMEM_LIMIT - 1024 - 256 - smem_extra - (long)g.nk * Shape<1>::A_KB_BYTES) / (Shape<1>::B_ST_BYTES / 2));
+      if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
+    }
     if (forced && forced < g.stages) g.stages = forced; }
   g.sched_mode = sched_mode;
   const long T = (long)g.row_blocks * g.col_tiles;
   const int sms = num_sms();
   if (sched_mode == 0) {
     g.splits = 1;
+    if (cg == 2) { const long pairs = sms / 2; return 2 * (int)(T < pairs ? T : pairs); }
     return (int)(T < sms ? T : sms);
   }
   // mode 1: every row block is cut into `splits` column ranges so that the grid covers the SMs
@@ -456,10 +562,11 @@ inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0) 
 
 template <class Epi>
 int launch_gram(const void* A, const void* B, int mh, const GramParams& g, const typename Epi::Params& ep, int grid,
-                cudaStream_t st) {
+                cudaStream_t st, int cg = 1) {
   EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "gram: K = %d leaves no shared memory for the B pipeline", g.nk * BK);
-  if (mh == 2) return launch_gram_mh<Epi, 2>(A, B, g, ep, grid, st);
-  return launch_gram_mh<Epi, 1>(A, B, g, ep, grid, st);
+  if (cg == 2) return launch_gram_mh<Epi, 1, 2>(A, B, g, ep, grid, st);
+  if (mh == 2) return launch_gram_mh<Epi, 2, 1>(A, B, g, ep, grid, st);
+  return launch_gram_mh<Epi, 1, 1>(A, B, g, ep, grid, st);
 }
 
 }  // namespace tc
