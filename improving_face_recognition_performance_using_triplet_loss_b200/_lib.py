@@ -43,7 +43,7 @@ SIGNATURES = {
     "efm_cosine_pairs": (_i, [_vp, _vp, _l, _l, _i, _vp, _vp]),
     "efm_cosine_pairs_indexed": (_i, [_vp, _vp, _vp, _l, _l, _i, _vp, _vp]),
     "efm_cosine_allpairs_workspace_bytes": (_sz, [_l, _l, _l, _i]),
-    "efm_cosine_allpairs": (_i, [_vp, _vp, _l, _l, _l, _i, _vp, _vp, _sz, _vp]),
+    "efm_cosine_allpairs": (_i, [_vp, _vp, _l, _l, _l, _i, _vp, _l, _vp, _sz, _vp]),
     "efm_bh_workspace_bytes": (_sz, [_l, _l, _l, _i, _i]),
     "efm_bh_triplet_fwd_bwd": (_i, [_vp, _vp, _l, _l, _l, _l, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "efm_bh_mine": (_i, [_vp, _l, _l, _l, _l, _i, _i, _vp, _sz, _vp]),

@@ -58,12 +58,13 @@ def cosine_allpairs(A: torch.Tensor, B: torch.Tensor | None = None) -> torch.Ten
     A2, B2 = A.contiguous(), B.contiguous()
     M, D = A2.shape
     N = B2.shape[0]
-    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ld = (N + 31) // 32 * 32                                # 128-byte aligned rows: every store hits whole sectors
+    buf = torch.empty((M, ld), dtype=torch.float32, device=A.device)
     dt = L.dtype_code(A2)
     ws = L.workspace(L.lib.efm_cosine_allpairs_workspace_bytes(M, N, D, dt), A.device)
     with torch.cuda.device(A.device):
-        L.check(L.lib.efm_cosine_allpairs(L.ptr(A2), L.ptr(B2), M, N, D, dt, L.ptr(out), L.ptr(ws), ws.numel(), L.stream()))
-    return out
+        L.check(L.lib.efm_cosine_allpairs(L.ptr(A2), L.ptr(B2), M, N, D, dt, L.ptr(buf), ld, L.ptr(ws), ws.numel(), L.stream()))
+    return buf[:, :N]                                       # view into the padded buffer (call .contiguous() if needed)
 
 
 def write_cosine_csv(path, pos, neg, mode="a+"):

@@ -372,7 +372,8 @@ struct StoreEpi {
   struct Params {
     const float* rna;   // (M) 1/|a_i|
     const float* rnb;   // (N) 1/|b_j|
-    float* out;         // (M, N)
+    float* out;         // (M, ld) with ld >= N
+    long ld;            // leading dimension of out in elements (a multiple of 32 keeps every 64-byte store sector-aligned)
   };
   struct State { float rna; int row0; };
   static __device__ __forceinline__ void row_begin(const Params& p, const tc::GramParams& g, int row, State& s) {
@@ -395,7 +396,7 @@ struct StoreEpi {
       for (int r = 0; r < 16; ++r) {
         const int lr = r + 16 * rsel;
         const int orow = s.row0 + lr;
-        if (orow < g.M) __stcs(&p.out[(long)orow * g.N + col], scratch[lr * 17 + c] * rb);
+        if (orow < g.M) __stcs(&p.out[(long)orow * p.ld + col], scratch[lr * 17 + c] * rb);
       }
     }
   }
@@ -593,9 +594,9 @@ extern "C" size_t efm_cosine_allpairs_workspace_bytes(long M, long N, long D, in
          align_up((size_t)N * 4, 256);
 }
 
-extern "C" int efm_cosine_allpairs(const void* A, const void* B, long M, long N, long D, int dtype, float* out,
+extern "C" int efm_cosine_allpairs(const void* A, const void* B, long M, long N, long D, int dtype, float* out, long ld_out,
                                    void* workspace, size_t ws_bytes, void* stream) {
-  EFM_REQUIRE(M >= 0 && N >= 0 && D > 0, EFM_E_ARG, "efm_cosine_allpairs: bad shape M=%ld N=%ld D=%ld", M, N, D);
+  EFM_REQUIRE(M >= 0 && N >= 0 && D > 0 && ld_out >= N, EFM_E_ARG, "efm_cosine_allpairs: bad shape M=%ld N=%ld D=%ld ld=%ld", M, N, D, ld_out);
   if (M == 0 || N == 0) return EFM_OK;
   EFM_REQUIRE(A && B && out && workspace, EFM_E_ARG, "efm_cosine_allpairs: null pointer");
   EFM_REQUIRE(aligned(workspace, 256), EFM_E_ALIGN, "efm_cosine_allpairs: workspace must be 256-byte aligned");
@@ -618,6 +619,6 @@ extern "C" int efm_cosine_allpairs(const void* A, const void* B, long M, long N,
   g.M = (int)M; g.N = (int)N; g.nk = Kp / tc::BK;
   const int mh = tc::pick_mh(g.M, g.nk);
   const int grid = tc::plan_gram(g, mh, 0, StoreEpi::SMEM_PER_WARP * tc::EPI_WARPS);
-  StoreEpi::Params ep{rna, rnb, out};
+  StoreEpi::Params ep{rna, rnb, out, ld_out};
   return tc::launch_gram<StoreEpi>(apad, bpad, mh, g, ep, grid, st);
 }

@@ -98,10 +98,11 @@ int efm_cosine_pairs(const void* a, const void* b, long P, long D, int dtype, fl
 /* gathered form for LFW-style pair lists: rows ia[k], ib[k] of one embedding matrix */
 int efm_cosine_pairs_indexed(const void* E, const int32_t* ia, const int32_t* ib, long P, long D, int dtype,
                              float* out, void* stream);
-/* all-pairs cosine matrix out[i][j] = cos(A_i, B_j), (M,N) fp32.  bf16 inputs run on tcgen05
- * (fp32 accumulate); needs workspace for padded operands + norms. */
+/* all-pairs cosine matrix out[i*ld_out + j] = cos(A_i, B_j), fp32, ld_out >= N (a multiple of 32 keeps the
+ * stores sector-aligned).  Operands are rounded to bf16 and run on tcgen05 (fp32 accumulate); needs workspace
+ * for padded operands + norms. */
 size_t efm_cosine_allpairs_workspace_bytes(long M, long N, long D, int dtype);
-int efm_cosine_allpairs(const void* A, const void* B, long M, long N, long D, int dtype, float* out,
+int efm_cosine_allpairs(const void* A, const void* B, long M, long N, long D, int dtype, float* out, long ld_out,
                         void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- a2': fused batch-hard triplet loss fwd+bwd (north_star; extends a1/a2) --------------------------
