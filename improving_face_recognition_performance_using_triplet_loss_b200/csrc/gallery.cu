@@ -270,14 +270,14 @@ pad_rows_kernel(const T* __restrict__ X, long rows, int D, int Kp, __nv_bfloat16
   }
 }
 
-__global__ void recip_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
+__global__ void recip_kernel(const float* __restrict__ x, long n, long npad, float* __restrict__ out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = 1.f / x[i];
+  if (i < npad) out[i] = i < n ? 1.f / x[i] : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------ tcgen05 top-K epilogue
 template <int KMAX> struct TopkEpi {
-  static constexpr int SMEM_PER_WARP = 0;
+  static constexpr int SMEM_PER_WARP = 2 * 256;      // double-buffered 1/gnorm of the warp's 64-column slice
   static constexpr int CW = 16;
   struct Params {
     const float* gnorm;   // (N) stored gallery norms
@@ -289,6 +289,7 @@ template <int KMAX> struct TopkEpi {
     float* part_s;        // (parts, nq, K)
     int32_t* part_i;
     int col_slices;       // 64-column slices per row half (4 for the 128x256 shape, 2 for 256x128)
+    int cg;               // CTAs per tile (2 = cta_group::2 pairs)
   };
   struct State {
     TopK<KMAX> tk;
@@ -301,16 +302,23 @@ template <int KMAX> struct TopkEpi {
     s.rqn = 1.f / s.qn;
     s.tk.init();
   }
+  // 1/gnorm of the warp's 64-column slice -> shared memory one tile ahead (lanes 0-15, 16 B each; rgn is padded)
+  static __device__ __forceinline__ void prefetch(const Params& p, const tc::GramParams&, float* scratch, int buf, int colw) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 16) tc::cp_async16(scratch + buf * 64 + lane * 4, p.rgn + colw + lane * 4);
+    tc::cp_async_commit();
+  }
+  static __device__ __forceinline__ void prefetch_wait() { tc::cp_async_wait_all(); __syncwarp(); }
   static __device__ __forceinline__ void chunk(const Params& p, const tc::GramParams& g, State& s, int row,
-                                               const uint32_t (&acc)[16], int col0, float*, int) {
+                                               const uint32_t (&acc)[16], int col0, float* scratch, int bc) {
     if (!s.valid) return;                            // padding rows of the last query block (their Gram is all zeros)
     const int ncols = g.N - col0;
     float est[16];                                   // g * (1/gnorm): cheap estimate of sim * |q|
     if (ncols >= 16) {
-      const float4* r4 = reinterpret_cast<const float4*>(p.rgn + col0);
+      const float4* r4 = reinterpret_cast<const float4*>(scratch + (bc >> 2) * 64 + (bc & 3) * 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 r = __ldg(r4 + q);
+        const float4 r = r4[q];
         est[4 * q + 0] = __uint_as_float(acc[4 * q + 0]) * r.x;
         est[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) * r.y;
         est[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) * r.z;
@@ -327,10 +335,11 @@ template <int KMAX> struct TopkEpi {
     float cut = p.sim_th;
     if (s.tk.full()) cut = fmaxf(cut, s.tk.s[KMAX - 1]);
     const float cutm = (cut - fabsf(cut) * 1e-5f - 1e-30f) * s.qn;   // compare g / gnorm against cut * |q|
-    bool anynan = false;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) anynan |= (est[k] != est[k]);
-    if (!(m >= cutm) && !anynan) return;
+    // NaN anywhere in the chunk?  fmaxf drops NaNs, a sum keeps them (FADDs on the under-used FMA pipe; inf - inf
+    // can only produce a false positive, which merely takes the exact path below)
+    const float nansum = ((est[0] + est[1]) + (est[2] + est[3])) + ((est[4] + est[5]) + (est[6] + est[7])) +
+                         (((est[8] + est[9]) + (est[10] + est[11])) + ((est[12] + est[13]) + (est[14] + est[15])));
+    if (!(m >= cutm) && !(nansum != nansum)) return;
     // rare: collect the surviving elements in a bit mask, then evaluate exactly (IEEE division) only those.
     // One copy of the insertion code, accumulators re-read from a local-memory copy by dynamic index (the fully
     // unrolled form made the kernel instruction-cache bound: 55 % stall_no_inst in ncu).
@@ -349,11 +358,9 @@ template <int KMAX> struct TopkEpi {
       if (accept_score(sim, p.sim_th, p.flags)) s.tk.insert(sim, col0 + k);
     }
   }
-  static __device__ __forceinline__ void prefetch(const Params&, const tc::GramParams&, float*, int, int) {}
-  static __device__ __forceinline__ void prefetch_wait() {}
   static __device__ __forceinline__ void row_end(const Params& p, const tc::GramParams& g, int row, int cs, State& s) {
     if (!s.valid) return;
-    const int part = (int)(blockIdx.x % g.splits) * p.col_slices + cs;                          // (split, column slice)
+    const int part = (int)((blockIdx.x / p.cg) % g.splits) * p.col_slices + cs;                          // (split, column slice)
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < p.K) {
@@ -420,7 +427,7 @@ TcOperands topk_tc_layout(long N, long D, long nq, int K, int parts_max) {
   L.gpad = take(L.copy_g ? (size_t)N * L.Kp * 2 : 0);
   L.qpad = take((size_t)nq * L.Kp * 2);
   L.qn = take((size_t)nq * 4);
-  L.rgn = take((size_t)N * 4);
+  L.rgn = take((size_t)cdiv(N, tc::BN) * tc::BN * 4);   // padded to whole column tiles (prefetched by 64-column slices)
   L.parts_s = take((size_t)parts_max * nq * K * 4);
   L.parts_i = take((size_t)parts_max * nq * K * 4);
   L.total = off;
@@ -490,9 +497,9 @@ extern "C" size_t efm_gallery_topk_workspace_bytes(long N, long D, long nq, int 
 }
 
 template <int KMAX>
-static int topk_tc_launch(const void* Gp, const void* Qp, int mh, tc::GramParams g, int grid,
+static int topk_tc_launch(const void* Gp, const void* Qp, int mh, int cg, tc::GramParams g, int grid,
                           const typename TopkEpi<KMAX>::Params& ep, cudaStream_t st) {
-  return tc::launch_gram<TopkEpi<KMAX>>(Qp, Gp, mh, g, ep, grid, st);
+  return tc::launch_gram<TopkEpi<KMAX>>(Qp, Gp, mh, g, ep, grid, st, cg);
 }
 
 extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long D, const void* Q, long nq, int K,
@@ -538,7 +545,8 @@ extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long 
   tc::GramParams g{};
   g.M = (int)nq; g.N = (int)N; g.nk = Kp / tc::BK;
   const int mh = tc::pick_mh(g.M, g.nk);
-  const int grid = tc::plan_gram(g, mh, 1);
+  const int cg = tc::pick_cg(g.M, mh, 1);
+  const int grid = tc::plan_gram(g, mh, 1, TopkEpi<1>::SMEM_PER_WARP * tc::EPI_WARPS, cg);
   const int col_slices = tc::EPI_SLICES / mh;
   const int parts = g.splits * col_slices;
   const TcOperands L = topk_tc_layout(N, D, nq, K, tc::EPI_SLICES * (int)cdiv(N, tc::BN));
@@ -558,19 +566,19 @@ extern "C" int efm_gallery_topk(const void* G, const float* gnorm, long N, long 
     pad_rows_kernel<__half><<<(unsigned)cdiv(nq, 8), 256, 0, st>>>((const __half*)Q, nq, (int)D, Kp, qpad, qn, nullptr);
   }
   EFM_LAUNCH_CHECK("pad_rows");
-  recip_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(gnorm, N, rgn);
+  recip_kernel<<<(unsigned)cdiv(cdiv(N, tc::BN) * tc::BN, 256), 256, 0, st>>>(gnorm, N, cdiv(N, tc::BN) * tc::BN, rgn);
   EFM_LAUNCH_CHECK("recip");
   const void* Gop = copy_g ? (const void*)gpad : G;
   int rc;
   if (K == 1) {
-    TopkEpi<1>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
-    rc = topk_tc_launch<1>(Gop, qpad, mh, g, grid, ep, st);
+    TopkEpi<1>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices, cg};
+    rc = topk_tc_launch<1>(Gop, qpad, mh, cg, g, grid, ep, st);
   } else if (K <= 5) {
-    TopkEpi<5>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
-    rc = topk_tc_launch<5>(Gop, qpad, mh, g, grid, ep, st);
+    TopkEpi<5>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices, cg};
+    rc = topk_tc_launch<5>(Gop, qpad, mh, cg, g, grid, ep, st);
   } else {
-    TopkEpi<EFM_GAL_MAX_K>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices};
-    rc = topk_tc_launch<EFM_GAL_MAX_K>(Gop, qpad, mh, g, grid, ep, st);
+    TopkEpi<EFM_GAL_MAX_K>::Params ep{gnorm, rgn, qn, sim_th, flags, K, idx_base, nq, ps, pi, col_slices, cg};
+    rc = topk_tc_launch<EFM_GAL_MAX_K>(Gop, qpad, mh, cg, g, grid, ep, st);
   }
   if (rc) return rc;
   return launch_topk_merge(ps, pi, parts, nq, K, out_score, out_idx, st);

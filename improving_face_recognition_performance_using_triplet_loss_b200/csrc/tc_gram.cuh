@@ -251,7 +251,8 @@ __device__ __forceinline__ void tile_range(const GramParams& g, long& t0, long& 
     t0 = c * T / G;
     t1 = (c + 1) * T / G;
   } else {
-    const long rb = blockIdx.x / g.splits, s = blockIdx.x % g.splits;
+    const long c = blockIdx.x / CG;
+    const long rb = c / g.splits, s = c % g.splits;
     t0 = rb * CT + s * CT / g.splits;
     t1 = rb * CT + (s + 1) * CT / g.splits;
   }
@@ -522,9 +523,10 @@ inline int pick_mh(int M, int nk) {
   return 1;
 }
 
-// 2-CTA pairs (cta_group::2): sched_mode 0 only, K-resident A, at least one full pair of row blocks
+// 2-CTA pairs (cta_group::2): 128 x 256 per-CTA shape, at least one full pair of row blocks
 inline int pick_cg(int M, int mh, int sched_mode) {
-  if (mh != 1 || sched_mode != 0 || M <= 128) return 1;
+  (void)sched_mode;
+  if (mh != 1 || M <= 128) return 1;
   if (const char* e = getenv("EFM_GRAM_CG")) { const int v = atoi(e); if (v == 1 || v == 2) return v; }
   return 2;
 }
@@ -553,11 +555,11 @@ inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0, 
     return (int)(T < sms ? T : sms);
   }
   // mode 1: every row block is cut into `splits` column ranges so that the grid covers the SMs
-  int splits = (int)cdiv((long)sms, g.row_blocks);                   // one wave of CTAs: fixed cost per CTA is ~8 us
+  int splits = (int)cdiv((long)(sms / cg), g.row_blocks);            // one wave of CTAs (pairs): fixed cost per CTA is ~8 us
   if (splits > g.col_tiles) splits = g.col_tiles;
   if (splits < 1) splits = 1;
   g.splits = splits;
-  return g.row_blocks * splits;
+  return g.row_blocks * splits * cg;
 }
 
 template <class Epi>
