@@ -231,15 +231,29 @@ def run_ours(args):
     barrier()
     ms = [s.elapsed_time(e) for s, e in evs]
     t_step = float(np.sum(ms)) / args.steps
-    # ---- dominant kernel alone (tcgen05 Gram + mining): launch-by-launch events, same L2 policy
+    # ---- dominant kernel alone (tcgen05 Gram + mining).  A ~30 us kernel timed launch-by-launch carries ~4-6 us of
+    # launch + event latency that is not kernel time (ncu gpu__time_duration of the same launch: 31-33 us), so each event
+    # pair brackets KREP back-to-back launches (L2 flushed before every group; the 4.2 MB of inputs are re-read from L2
+    # by the later launches of a group exactly as they are inside the step, where bh_prep has just written them).
+    KREP = 5
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for s, e in kev:
+        flush.zero_()
+        s.record(stream)
+        for _ in range(KREP):
+            L.check(L.lib.efm_bh_mine(L.ptr(E_all), G, lo, B, DIM, dt, flags, L.ptr(ws), ws.numel(), L.stream()))
+        e.record(stream)
+    barrier()
+    t_kernel = float(np.mean([s.elapsed_time(e) for s, e in kev])) / KREP
+    # single launches (flush before each) for reference
+    kev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 20))]
+    for s, e in kev1:
         flush.zero_()
         s.record(stream)
         L.check(L.lib.efm_bh_mine(L.ptr(E_all), G, lo, B, DIM, dt, flags, L.ptr(ws), ws.numel(), L.stream()))
         e.record(stream)
     barrier()
-    t_kernel = float(np.mean([s.elapsed_time(e) for s, e in kev]))
+    t_kernel_single = float(np.mean([s.elapsed_time(e) for s, e in kev1]))
     clocks = sampler.stop()
 
     # ---- e2e: public API, pinned host buffers in, loss + indices out, every step (wall clock)
@@ -270,9 +284,9 @@ def run_ours(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([t_step, t_kernel, t_e2e * 1e3], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_step, t_kernel, t_e2e * 1e3, t_kernel_single], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_step, t_kernel, t_e2e = float(t[0]), float(t[1]), float(t[2]) / 1e3
+        t_step, t_kernel, t_e2e, t_kernel_single = float(t[0]), float(t[1]), float(t[2]) / 1e3, float(t[3])
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -294,12 +308,13 @@ def run_ours(args):
             },
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "gram_kernel<MineEpi> (tcgen05 Gram + batch-hard mining epilogue)",
-                         "kernel_ms": t_kernel, "flops_per_launch": flops, "peak_source": pk_src + ", burst bf16"},
+                         "kernel_ms": t_kernel, "kernel_ms_single_launch": t_kernel_single, "launches_per_event_pair": KREP,
+                         "flops_per_launch": flops, "peak_source": pk_src + ", burst bf16"},
             "e2e": {"value": G / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(E_host.numel() * 2 + y_host.numel() * 4),
                     "d2h_bytes_per_step": int(B * 12), "ms_per_step": t_e2e * 1e3,
                     "how": "public API batch_hard_triplet(), pinned host E+labels -> device, loss+idx_p+idx_n -> pinned host, "
                            "stream sync every step, wall clock"},
-            "gpu_launches": 4 * args.steps, "launches_per_step": ["bh_prep", "gram_kernel<MineEpi>", "bh_finalize", "bh_grad"], "memsets_per_step": 1,
+            "gpu_launches": 4 * args.steps,   # kernels of the timed steps (the roofline / e2e loops launch theirs on top) "launches_per_step": ["bh_prep", "gram_kernel<MineEpi>", "bh_finalize", "bh_grad"], "memsets_per_step": 1,
             "clocks": clocks,
             "pairs_per_s": (float(B) * G * world) / (t_step * 1e-3),
         }

@@ -46,6 +46,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;        // 227 KB opt-in maximum per CTA
 
 struct GramParams {
+  unsigned long long* trace;   // profiling aid (env EFM_GRAM_TRACE=<device ptr>): 8 globaltimer stamps per CTA
   int debug;             // profiling aid (env EFM_GRAM_DEBUG): 1 = skip the epilogue work, 2 = TMEM loads only
   int M, N;              // valid rows of A / rows of B (= Gram columns)
   int nk;                // K blocks of 64 (Kp = 64 * nk)
@@ -140,6 +141,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define EFM_TRACE(slot) do { if (g.trace && (threadIdx.x & 31) == 0) g.trace[(size_t)blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile(
@@ -314,6 +317,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) EFM_TRACE(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -331,6 +335,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers + TMEM of both CTAs are live past this point
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) EFM_TRACE(1);
 
   long t0l, t1l;
   tile_range<CG>(g, t0l, t1l);
@@ -371,6 +376,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
+      if (i == 0) EFM_TRACE(2);
       if (++ct == CT) { ct = 0; ++rb; }
     }
   } else if (warp == MMA_WARP && crank == 0) {
@@ -418,6 +424,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (last_of_rb) umma_commit(bar_a_empty);                  // A row-block may be overwritten
         }
       }
+      if (i + 1 == ntiles) EFM_TRACE(5);
       if (++ct == CT) ct = 0;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -446,6 +453,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         Epi::prefetch(ep, g, scratch, (i + 1) & 1, (ct + 1 == CT ? 0 : ct + 1) * BN + cs * COLS_PER_WARP);
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
+      if (i == 0 && warp == 0) EFM_TRACE(3);
       const uint32_t t_acc = tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + rowhalf * BN + cs * COLS_PER_WARP);
       if ((g.debug & 3) != 1) {
 #pragma unroll
@@ -465,6 +473,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (CG == 2) mbar_arrive_cluster(bar_acc_empty + 8 * acc, 0);   // the leader's MMA thread waits for both CTAs
         else mbar_arrive(bar_acc_empty + 8 * acc);
       }
+      if (warp == 0) { if (i == 0) EFM_TRACE(4); if (i + 1 == ntiles) EFM_TRACE(6); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (++ct == CT) { ct = 0; ++rb; }
     }
@@ -478,6 +487,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncwarp();
     if constexpr (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) EFM_TRACE(7);
 }
 
 // ---- host side: tensor maps + launch ----------------------------------------------------------------------
@@ -535,6 +545,7 @@ inline int pick_cg(int M, int mh, int sched_mode) {
 inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0, int cg = 1) {
   const int bm = 128 * mh * cg, bn = 256 / mh;
   { const char* e = getenv("EFM_GRAM_DEBUG"); g.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("EFM_GRAM_TRACE"); g.trace = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   g.stages = 0;
   if (const char* e = getenv("EFM_GRAM_STAGES")) { const int v = atoi(e); if (v >= 1) g.stages = -v; }
   g.row_blocks = (int)cdiv(g.M, bm);
