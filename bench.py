@@ -291,6 +291,11 @@ def run_ours(args):
     if rank == 0:
         pk, pk_src = peaks()
         flops = 2.0 * B * G * DIM                                      # full Gram strip, symmetry not credited
+        traffic = None                                                 # dram bytes of one launch, from the committed ncu capture
+        tf = os.path.join(ROOT, "profiles", "r1_gram_final_summary.json")
+        if world == 1 and not strong and os.path.exists(tf):
+            with open(tf) as f:
+                traffic = json.load(f).get("traffic_bytes_per_launch")
         achieved = flops / (t_kernel * 1e-3) / 1e12
         peak = float(pk["bf16_tflops"])                                # burst figure: kernel timed alone
         line = {
@@ -307,7 +312,7 @@ def run_ours(args):
                 "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks",
             },
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gram_kernel<MineEpi> (tcgen05 Gram + batch-hard mining epilogue)",
+                         "traffic": traffic, "kernel": "gram_kernel<MineEpi> (tcgen05 Gram + batch-hard mining epilogue)",
                          "kernel_ms": t_kernel, "kernel_ms_single_launch": t_kernel_single, "launches_per_event_pair": KREP,
                          "flops_per_launch": flops, "peak_source": pk_src + ", burst bf16"},
             "e2e": {"value": G / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(E_host.numel() * 2 + y_host.numel() * 4),
