@@ -49,6 +49,8 @@ SIGNATURES = {
     "efm_bh_mine": (_i, [_vp, _l, _l, _l, _l, _i, _i, _vp, _sz, _vp]),
     "efm_bh_backward_workspace_bytes": (_sz, [_l]),
     "efm_bh_backward": (_i, [_vp, _l, _l, _l, _l, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "efm_bh_grad_rows_workspace_bytes": (_sz, [_l, _l]),
+    "efm_bh_grad_rows": (_i, [_vp, _l, _l, _i, _i, _vp, _vp, _vp, _l, _l, _vp, _vp, _sz, _vp]),
     "efm_gallery_scores_f32": (_i, [_vp, _vp, _l, _l, _vp, _l, _vp, _vp]),
     "efm_simd_dot_rows": (_i, [_vp, _l, _l, _vp, _l, _vp, _vp]),
     "efm_simd_norm_rows": (_i, [_vp, _l, _l, _vp, _vp]),

@@ -531,9 +531,17 @@ __global__ void __launch_bounds__(WARPS * 32, 6)
 bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int normalize, long B_all, int D,
                long row_offset, long B_local, const int32_t* __restrict__ idx_p, const int32_t* __restrict__ idx_n,
                const float* __restrict__ wgt, const int32_t* __restrict__ rheadp, const int32_t* __restrict__ rheadn,
-               const int32_t* __restrict__ rnextp, const int32_t* __restrict__ rnextn, float* __restrict__ dE) {
-  const long r = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (r >= B_all) return;
+               const int32_t* __restrict__ rnextp, const int32_t* __restrict__ rnextn, float* __restrict__ dE,
+               long row_begin) {
+  // rows [row_begin, row_begin + B_all) are processed (B_all = number of output rows); anchors are rows
+  // [row_offset, row_offset + B_local) and index idx_p / idx_n / wgt / rnext*; rhead* and dE are indexed by the
+  // processed row (r - row_begin).  Fused single-call form: row_begin = 0, B_all = all rows.  Row-sliced form
+  // (efm_bh_grad_rows): row_begin = first local row, anchors = every row of the gathered batch.
+  const long rl = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (rl >= B_all) return;
+  const long r = row_begin + rl;
+  dE += -row_begin * D;                                           // dE[r * D] addresses output row r - row_begin
+  rheadp -= row_begin; rheadn -= row_begin;
   const int lane = threadIdx.x & 31;
   const T* er = E + r * D;
   const float nr = normalize ? 1.f / nrm[r] : 1.f;              // reciprocal norm of this row
@@ -725,9 +733,9 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   if (dE_all) {
     EFM_DISPATCH_DTYPE(dtype, T, {
       if (vec) bh_grad_kernel<T, 8><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                                      B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
+                                                                      B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0);
       else bh_grad_kernel<T, 1><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                                  B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
+                                                                  B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0);
     });
     EFM_LAUNCH_CHECK("bh_grad");
   }
@@ -790,11 +798,85 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
   }
   EFM_DISPATCH_DTYPE(dtype, T, {
     if (vec) bh_grad_kernel<T, 8><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                                    B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
+                                                                    B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0);
     else bh_grad_kernel<T, 1><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                                B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all);
+                                                                B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0);
   });
   EFM_LAUNCH_CHECK("bh_grad");
+  return EFM_OK;
+}
+
+// ---- multi-GPU exact gradient without a dense reduce-scatter ----------------------------------------------------------
+// Every rank all-gathers (idx_p, idx_n, wgt) of all anchors (12 bytes per anchor) and computes the gradient of ITS rows
+// only: the anchor-role term of its own anchors plus the positive / negative-role terms of every anchor (of any rank)
+// that picked one of its rows.  All embeddings needed are in the gathered batch already.
+__global__ void __launch_bounds__(256)
+bh_chain_kernel(const int32_t* __restrict__ idx_p, const int32_t* __restrict__ idx_n, const float* __restrict__ wgt,
+                long n_anchors, long row_begin, long nrows, int32_t* __restrict__ rheadp, int32_t* __restrict__ rheadn,
+                int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn) {
+  const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_anchors || wgt[j] == 0.f) return;
+  const long p = idx_p[j] - row_begin, n = idx_n[j] - row_begin;
+  if (p >= 0 && p < nrows) rnextp[j] = atomicExch(&rheadp[p], (int32_t)j);
+  if (n >= 0 && n < nrows) rnextn[j] = atomicExch(&rheadn[n], (int32_t)j);
+}
+
+struct GradRowsLayout { size_t nrm, sq, rheadp, rheadn, rnextp, rnextn, total; };
+static GradRowsLayout grad_rows_layout(long B_all, long B_local) {
+  GradRowsLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.nrm = take((size_t)B_all * 4); L.sq = take((size_t)B_all * 4);
+  L.rheadp = take((size_t)B_local * 4); L.rheadn = take((size_t)B_local * 4);
+  L.rnextp = take((size_t)B_all * 4); L.rnextn = take((size_t)B_all * 4);
+  L.total = off;
+  return L;
+}
+extern "C" size_t efm_bh_grad_rows_workspace_bytes(long B_all, long B_local) {
+  return grad_rows_layout(B_all > 0 ? B_all : 0, B_local > 0 ? B_local : 0).total;
+}
+
+extern "C" int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype, int flags, const int32_t* idx_p_all,
+                                const int32_t* idx_n_all, const float* wgt_all, long row_offset, long B_local,
+                                float* dE_local, void* workspace, size_t ws_bytes, void* stream) {
+  EFM_REQUIRE(B_all > 0 && B_local >= 0 && D > 0 && row_offset >= 0 && row_offset + B_local <= B_all, EFM_E_ARG,
+              "efm_bh_grad_rows: bad shape B_all=%ld row_offset=%ld B_local=%ld D=%ld", B_all, row_offset, B_local, D);
+  if (B_local == 0) return EFM_OK;
+  EFM_REQUIRE(E_all && idx_p_all && idx_n_all && wgt_all && dE_local && workspace, EFM_E_ARG, "efm_bh_grad_rows: null pointer");
+  EFM_REQUIRE(aligned(workspace, 256), EFM_E_ALIGN, "efm_bh_grad_rows: workspace must be 256-byte aligned");
+  const GradRowsLayout L = grad_rows_layout(B_all, B_local);
+  EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_grad_rows: workspace %zu < required %zu", ws_bytes, L.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* nrm = reinterpret_cast<float*>(ws + L.nrm);
+  float* sq = reinterpret_cast<float*>(ws + L.sq);
+  int32_t* rheadp = reinterpret_cast<int32_t*>(ws + L.rheadp);
+  int32_t* rheadn = reinterpret_cast<int32_t*>(ws + L.rheadn);
+  int32_t* rnextp = reinterpret_cast<int32_t*>(ws + L.rnextp);
+  int32_t* rnextn = reinterpret_cast<int32_t*>(ws + L.rnextn);
+  const int normalize = (flags & EFM_BH_NORMALIZE) ? 1 : 0;
+  const bool vec = bh_vec8(E_all, D, dE_local);
+  EFM_CUDA(cudaMemsetAsync(ws + L.rheadp, 0xFF, L.rnextp - L.rheadp, st));
+  if (normalize) {                                                // row norms of the whole gathered batch
+    EFM_BH_DISPATCH(dtype, vec, T, V, {
+      bh_prep_kernel<T, V><<<(unsigned)cdiv(B_all, WARPS), WARPS * 32, 0, st>>>((const T*)E_all, nullptr, B_all, (int)D, (int)D, 1,
+                                                                                 0, 0, 0, 0, sq, nrm, nullptr, nullptr, nullptr, nullptr,
+                                                                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                                 nullptr, nullptr, 0);
+    });
+    EFM_LAUNCH_CHECK("bh_prep(stats)");
+  }
+  bh_chain_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(idx_p_all, idx_n_all, wgt_all, B_all, row_offset, B_local, rheadp,
+                                                                rheadn, rnextp, rnextn);
+  EFM_LAUNCH_CHECK("bh_chain");
+  const unsigned grid = (unsigned)cdiv(B_local, WARPS);
+  EFM_DISPATCH_DTYPE(dtype, T, {
+    if (vec) bh_grad_kernel<T, 8><<<grid, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_local, (int)D, 0, B_all, idx_p_all,
+                                                                idx_n_all, wgt_all, rheadp, rheadn, rnextp, rnextn, dE_local, row_offset);
+    else bh_grad_kernel<T, 1><<<grid, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_local, (int)D, 0, B_all, idx_p_all,
+                                                            idx_n_all, wgt_all, rheadp, rheadn, rnextp, rnextn, dE_local, row_offset);
+  });
+  EFM_LAUNCH_CHECK("bh_grad(rows)");
   return EFM_OK;
 }
 

@@ -3,8 +3,9 @@
 * global batch-hard mining: all-gather of embeddings + labels (NCCL over NVLink on GPUs, gloo in CPU tests of
   the host logic), every rank mines its B/P x B strip against the global batch; row extrema are complete per
   rank, so mining needs no reduction.  Exact mode reduce-scatters dE_all so the result equals the single-GPU
-  loss on the concatenated batch; detached mode (reference-faithful, negatives are constants) needs no
-  backward collective.
+  loss on the concatenated batch WITHOUT a dense reduce-scatter (12 bytes per anchor are all-gathered instead and
+  every rank evaluates the terms that land on its own rows); detached mode (reference-faithful, negatives are
+  constants) needs no backward collective.
 * sharded gallery top-k: each rank owns a contiguous row shard, local top-k with global indices, all-gather of
   (score, idx) lists and a K-way merge on every rank.
 """
@@ -30,22 +31,37 @@ def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def global_batch_hard(E_local: torch.Tensor, labels_local: torch.Tensor, margin: float, *, normalize=True,
-                      exact_grad=True, mine_bf16=None, group=None, _impl=None):
+                      exact_grad=True, mine_bf16=None, head_grad=None, group=None, _impl=None, _grad_rows=None):
     """Batch-hard triplet loss over the global batch.  Returns (loss_local (B,), idx_p, idx_n (global row
-    indices), dE_local (B, D) fp32).  `_impl` lets the CPU tests substitute the single-process operator."""
-    from .loss import batch_hard_triplet
+    indices), dE_local (B, D) fp32).
+
+    exact_grad=True  -> the gradient equals the single-GPU gradient of the concatenated batch.  No dense
+        reduce-scatter: every rank all-gathers 12 bytes per anchor (idx_p, idx_n, weight) and evaluates the
+        positive / negative-role terms that land on ITS rows from the already gathered embeddings.
+    exact_grad=False -> gathered rows are constants (mirrors the reference's detached negatives): no backward collective.
+    `_impl` / `_grad_rows` let the CPU tests substitute the single-process operators."""
+    from .loss import batch_hard_grad_rows, batch_hard_triplet
     impl = _impl or batch_hard_triplet
+    grad_rows = _grad_rows or batch_hard_grad_rows
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     B = E_local.shape[0]
     E_all = all_gather_rows(E_local, group)
     y_all = all_gather_rows(labels_local.reshape(-1).to(torch.int32), group)
-    loss, idx_p, idx_n, dE_all = impl(E_all, y_all, margin, normalize=normalize, row_offset=rank * B, num_local=B,
-                                      want_grad=True, detach_gathered=not exact_grad, mine_bf16=mine_bf16)
-    if exact_grad and world > 1:
-        dE_local = torch.empty((B, E_local.shape[1]), dtype=dE_all.dtype, device=dE_all.device)
-        dist.reduce_scatter_tensor(dE_local, dE_all.contiguous(), op=dist.ReduceOp.SUM, group=group)
-    else:
-        dE_local = dE_all[rank * B:(rank + 1) * B]
+    if not exact_grad or world == 1:
+        loss, idx_p, idx_n, dE_all = impl(E_all, y_all, margin, normalize=normalize, row_offset=rank * B, num_local=B,
+                                          want_grad=True, detach_gathered=not exact_grad, mine_bf16=mine_bf16,
+                                          head_grad=head_grad)
+        return loss, idx_p, idx_n, dE_all[rank * B:(rank + 1) * B]
+    loss, idx_p, idx_n, _ = impl(E_all, y_all, margin, normalize=normalize, row_offset=rank * B, num_local=B,
+                                 want_grad=False, mine_bf16=mine_bf16)
+    w = torch.where(loss > 0, torch.full_like(loss, 2.0), torch.zeros_like(loss))       # relu'(0) = 0
+    if head_grad is not None:
+        w = w * head_grad.to(w.dtype)
+    packed = torch.stack([idx_p.to(torch.int32), idx_n.to(torch.int32), w.to(torch.float32).view(torch.int32)])  # (3, B)
+    allp = all_gather_rows(packed.unsqueeze(0), group)                                   # (world, 3, B)
+    ip_all = allp[:, 0].reshape(-1); in_all = allp[:, 1].reshape(-1)
+    w_all = allp[:, 2].reshape(-1).contiguous().view(torch.float32)
+    dE_local = grad_rows(E_all, ip_all, in_all, w_all, row_offset=rank * B, num_local=B, normalize=normalize)
     return loss, idx_p, idx_n, dE_local
 
 

@@ -168,6 +168,28 @@ def batch_hard_backward(E_all, idx_p, idx_n, margin, head_grad, *, normalize=Tru
     return dE
 
 
+def batch_hard_grad_rows(E_all, idx_p_all, idx_n_all, wgt_all, *, row_offset=0, num_local=None, normalize=True):
+    """Exact gradient for rows [row_offset, row_offset+num_local) of the gathered batch from the gathered mining
+    results of EVERY anchor (anchor j = row j): wgt_all[j] = 2 * head_grad_j where loss_j > 0, else 0.  This is the
+    multi-GPU backward without a dense reduce-scatter (see distributed.global_batch_hard).  Returns (num_local, D) fp32."""
+    L.require_cuda(E_all, idx_p_all, idx_n_all, wgt_all)
+    E_all = E_all.contiguous()
+    B_all, D = E_all.shape
+    B = B_all - row_offset if num_local is None else int(num_local)
+    dev = E_all.device
+    ip = idx_p_all.to(torch.int32).contiguous(); inn = idx_n_all.to(torch.int32).contiguous()
+    w = wgt_all.to(torch.float32).contiguous()
+    if not (ip.numel() == inn.numel() == w.numel() == B_all):
+        raise ValueError("idx_p_all / idx_n_all / wgt_all must have one entry per row of E_all")
+    ws = L.workspace(L.lib.efm_bh_grad_rows_workspace_bytes(B_all, B), dev)
+    dE = torch.empty((B, D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib.efm_bh_grad_rows(L.ptr(E_all), B_all, D, L.dtype_code(E_all), _bh_flags(normalize, False, False),
+                                       L.ptr(ip), L.ptr(inn), L.ptr(w), int(row_offset), B, L.ptr(dE), L.ptr(ws),
+                                       ws.numel(), L.stream()))
+    return dE
+
+
 class _BatchHard(torch.autograd.Function):
     """reduction 'sum'/'mean': gradient is produced by the SAME fused call as the loss (head-grad ones) and
     scaled by the incoming scalar in backward.  reduction 'none': forward only; backward re-runs the cheap

@@ -130,6 +130,15 @@ int efm_bh_backward(const void* E_all, long B_all, long row_offset, long B_local
                     float margin, const float* head_grad, int flags, const int32_t* idx_p,
                     const int32_t* idx_n, float* dE_all, void* workspace, size_t ws_bytes, void* stream);
 
+/* Multi-GPU exact gradient without a dense reduce-scatter: given the all-gathered batch and the all-gathered
+ * (idx_p, idx_n, wgt) of EVERY anchor (anchor j = row j; wgt_j = 2 * head_grad_j if loss_j > 0 else 0), compute
+ * dE for rows [row_offset, row_offset+B_local) only -- anchor-role terms of the local anchors plus the positive /
+ * negative-role terms of all anchors (of any rank) that mined one of these rows.  dE_local: (B_local, D) fp32. */
+size_t efm_bh_grad_rows_workspace_bytes(long B_all, long B_local);
+int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype, int flags, const int32_t* idx_p_all,
+                     const int32_t* idx_n_all, const float* wgt_all, long row_offset, long B_local,
+                     float* dE_local, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- a8-a11: gallery scoring ---------------------------------------------------------------------
  * simd_dot (Feature.hpp:273-293) + Compare_Face_From_DB (:345-392 argmax, :295-343 top-K) +
  * Compare_Face_Person/Compare_Face_DB (:763-804).  G: (N,D), gnorm: (N,) stored row norms

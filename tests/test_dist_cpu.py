@@ -49,6 +49,21 @@ def _oracle_impl(E_all, y_all, margin, *, normalize=True, row_offset=0, num_loca
             torch.from_numpy(dE).float())
 
 
+def _oracle_grad_rows(E_all, ip_all, in_all, w_all, *, row_offset=0, num_local=None, normalize=True):
+    """Row-sliced exact gradient (oracle): every anchor's contribution that lands on rows [row_offset, +num_local)."""
+    E = E_all.double().numpy(); ip = ip_all.numpy(); inn = in_all.numpy(); w = w_all.double().numpy()
+    nrm = np.sqrt((E * E).sum(1, keepdims=True)) if normalize else np.ones((E.shape[0], 1))
+    X = E / nrm
+    dX = np.zeros_like(X)
+    for j in range(E.shape[0]):
+        if w[j] == 0:
+            continue
+        p, n = ip[j], inn[j]
+        dX[j] += w[j] * (X[n] - X[p]); dX[p] += w[j] * (X[p] - X[j]); dX[n] += w[j] * (X[j] - X[n])
+    dE = (dX - X * (X * dX).sum(1, keepdims=True)) / nrm if normalize else dX
+    return torch.from_numpy(dE[row_offset:row_offset + num_local]).float()
+
+
 def _numpy_merge(ps, pi):
     parts, nq, K = ps.shape
     out_s = torch.zeros(nq, K); out_i = torch.full((nq, K), -1, dtype=torch.int32)
@@ -70,7 +85,8 @@ def _worker(rank, world, port, out):
     El = torch.from_numpy(E[rank * B:(rank + 1) * B]); yl = torch.from_numpy(y[rank * B:(rank + 1) * B])
     res = {}
     for exact in (True, False):
-        loss, ip, inn, dE = D.global_batch_hard(El, yl, 1.9, normalize=True, exact_grad=exact, _impl=_oracle_impl)
+        loss, ip, inn, dE = D.global_batch_hard(El, yl, 1.9, normalize=True, exact_grad=exact, _impl=_oracle_impl,
+                                                _grad_rows=_oracle_grad_rows)
         res["exact" if exact else "detached"] = (loss.numpy(), ip.numpy(), inn.numpy(), dE.numpy())
     # sharded gallery: every rank scores its shard, lists carry global indices
     rng = np.random.default_rng(0)
@@ -99,7 +115,7 @@ def test_global_batch_hard_and_sharded_topk_world2():
     ip = np.concatenate([out[r]["exact"][1] for r in range(world)])
     dE = np.concatenate([out[r]["exact"][3] for r in range(world)])
     assert np.allclose(loss, full["loss"], atol=1e-5) and np.array_equal(ip, full["idx_p"])
-    assert np.allclose(dE, full["dE_all"], atol=1e-5)                   # reduce-scatter == single-process gradient
+    assert np.allclose(dE, full["dE_all"], atol=1e-5)                   # sparse exchange == single-process gradient
     # detached mode: each rank's gradient covers only its own rows and ignores remote positive/negative roles
     for r in range(world):
         assert out[r]["detached"][3].shape == (16, 8)

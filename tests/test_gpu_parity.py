@@ -312,6 +312,22 @@ def test_bh_strip_equals_full_batch(P, dtype):
     assert not d[:128].any() and not d[256:].any() and d[128:256].any()
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bh_row_sliced_gradient_equals_full(P, dtype):
+    """Multi-GPU exact backward on one device: per-'rank' forward, 'all-gather' of (idx_p, idx_n, wgt), row-sliced
+    gradient per rank == the gradient of the single fused call on the whole batch."""
+    E, y = clustered(512, 128, seed=31)
+    Et, yt = dev(E, dtype), dev(y)
+    loss, ip, inn, dE = P.batch_hard_triplet(Et, yt, 1.9)
+    assert (loss > 0).sum() > 64
+    w = torch.where(loss > 0, 2.0, 0.0) * torch.linspace(0.5, 1.5, 512).cuda()          # non-trivial head gradient
+    full = P.batch_hard_backward(Et, ip, inn, 1.9, w / 2)
+    parts = [P.batch_hard_grad_rows(Et, ip, inn, w, row_offset=r * 128, num_local=128) for r in range(4)]
+    assert rel_err(torch.cat(parts).cpu().numpy(), full.cpu().numpy()) < 1e-5
+    ref = O.batch_hard_triplet(Et.float().cpu().numpy(), y, 1.9, head_grad=(w / 2).cpu().numpy(), mine_bf16=(dtype != torch.float32))
+    assert rel_err(torch.cat(parts).cpu().numpy(), ref["dE_all"]) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
 def test_bh_autograd_module(P):
     E, y = clustered(256, 64, seed=5)
     for red in ("none", "sum", "mean"):
