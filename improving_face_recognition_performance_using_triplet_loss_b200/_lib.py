@@ -51,6 +51,16 @@ SIGNATURES = {
     "efm_bh_backward": (_i, [_vp, _l, _l, _l, _l, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "efm_bh_grad_rows_workspace_bytes": (_sz, [_l, _l]),
     "efm_bh_grad_rows": (_i, [_vp, _l, _l, _i, _i, _vp, _vp, _vp, _l, _l, _vp, _vp, _sz, _vp]),
+    "efm_bh_xchg_bytes": (_sz, [_l, _i, _l, _i]),
+    "efm_bh_dist_workspace_bytes": (_sz, [_l, _i]),
+    "efm_xchg_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "efm_xchg_free": (_i, [_vp]),
+    "efm_ipc_export": (_i, [_vp, C.c_char_p]),
+    "efm_ipc_import": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "efm_ipc_release": (_i, [_vp]),
+    "efm_bh_dist_fwd_bwd": (_i, [_vp, _vp, _l, _l, _i, _f, _vp, _i, _i, _i, C.POINTER(_vp), C.c_ulonglong, _vp, _vp, _vp, _vp,
+                                 _vp, _sz, _vp]),
+    "efm_bh_profile_events": (_i, [_vp, _vp]),
     "efm_gallery_scores_f32": (_i, [_vp, _vp, _l, _l, _vp, _l, _vp, _vp]),
     "efm_simd_dot_rows": (_i, [_vp, _l, _l, _vp, _l, _vp, _vp]),
     "efm_simd_norm_rows": (_i, [_vp, _l, _l, _vp, _vp]),

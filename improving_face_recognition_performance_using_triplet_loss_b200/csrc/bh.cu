@@ -11,6 +11,8 @@
 //   3. bh_finalize  per anchor: decode indices, recompute d_ap, d_an directly in fp32 (no Gram
 //                   cancellation), hinge, scatter-add 2w(n-p), 2w(p-a), 2w(a-n) into dE
 //   4. bh_norm_bwd  (normalize only) dE = (dX - x (x . dX)) / |e| in place
+#include <string.h>
+
 #include "tc_gram.cuh"
 
 namespace efm {
@@ -72,6 +74,43 @@ template <typename T> __device__ __forceinline__ void load8(const T* p, float (&
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
   }
+}
+
+// ------------------------------------------------------------------------------------------ per-label member table
+// register `row` with its label: open-addressing table of 64-bit tags; the first 8 members of a label are stored
+// inline (no pointer chasing in bh_finalize), further members go to an overflow chain
+__device__ __forceinline__ void label_table_insert(int32_t lab, long row, unsigned long long* __restrict__ hkeys,
+                                                   int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem,
+                                                   int32_t* __restrict__ hhead, int32_t* __restrict__ hnext,
+                                                   int32_t* __restrict__ hslot, int tbits) {
+  const unsigned long long tag = (unsigned long long)(uint32_t)lab;     // upper half 0: never equals EMPTY (~0)
+  const uint32_t mask = (1u << tbits) - 1u;
+  uint32_t sl = ((uint32_t)lab * 2654435761u) >> (32 - tbits);
+  for (;;) {
+    const unsigned long long old = atomicCAS(&hkeys[sl], ~0ull, tag);
+    if (old == ~0ull || old == tag) break;
+    sl = (sl + 1) & mask;
+  }
+  hslot[row] = (int32_t)sl;
+  const int pos = atomicAdd(&hcnt[sl], 1) + 1;                       // counter starts at -1
+  if (pos < 8) hmem[sl * 8 + pos] = (int32_t)row;
+  else hnext[row] = atomicExch(&hhead[sl], (int32_t)row);
+}
+
+// Multi-GPU step: the labels of the peers' rows arrive during the Gram kernel, so the table is built afterwards, one
+// thread per row.  Every block first waits until all `world` arrival counters (stage B of the exchange: the original
+// rows bh_finalize reads next) have reached `target`; stream order then covers the kernels that follow.
+__global__ void __launch_bounds__(256)
+bh_label_table_kernel(const int32_t* __restrict__ lab, long B_all, unsigned long long* __restrict__ hkeys,
+                      int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem, int32_t* __restrict__ hhead,
+                      int32_t* __restrict__ hnext, int32_t* __restrict__ hslot, int tbits,
+                      const unsigned long long* __restrict__ cnt, int world, unsigned long long target) {
+  if (cnt) {
+    if ((int)threadIdx.x < world) tc::wait_counter_thread(cnt + threadIdx.x, target);
+    __syncthreads();
+  }
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < B_all) label_table_insert(lab[row], row, hkeys, hcnt, hmem, hhead, hnext, hslot, tbits);
 }
 
 // ------------------------------------------------------------------------------------------ prep
@@ -197,20 +236,7 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
     }
     const long li = row - row_offset;
     if (kpos && li >= 0 && li < B_local) { kpos[li] = KEY_POS_EMPTY; kneg[li] = KEY_NEG_EMPTY; }
-    if (hkeys) {                                     // register this row with its label (open-addressing table)
-      const unsigned long long tag = (unsigned long long)(uint32_t)lab;     // upper half 0: never equals EMPTY (~0)
-      const uint32_t mask = (1u << tbits) - 1u;
-      uint32_t sl = ((uint32_t)lab * 2654435761u) >> (32 - tbits);
-      for (;;) {
-        const unsigned long long old = atomicCAS(&hkeys[sl], ~0ull, tag);
-        if (old == ~0ull || old == tag) break;
-        sl = (sl + 1) & mask;
-      }
-      hslot[row] = (int32_t)sl;
-      const int pos = atomicAdd(&hcnt[sl], 1) + 1;                   // counter starts at -1
-      if (pos < 8) hmem[sl * 8 + pos] = (int32_t)row;                // inline member list: no pointer chasing later
-      else hnext[row] = atomicExch(&hhead[sl], (int32_t)row);        // overflow chain (labels with > 8 rows)
-    }
+    if (hkeys) label_table_insert(lab, row, hkeys, hcnt, hmem, hhead, hnext, hslot, tbits);
   }
 }
 
@@ -367,6 +393,14 @@ bh_mine_f32_kernel(const float* __restrict__ X, const float* __restrict__ sq, co
 }
 
 // ------------------------------------------------------------------------------------------ finalize
+// Multi-GPU exact gradient (see efm_bh_dist_fwd_bwd): where bh_finalize publishes an anchor's mining result.
+struct ResPush {
+  int world, rank;                              // world = 0: nothing to publish
+  int32_t* ip[tc::MAX_PEERS];                   // (B_all) arrays inside rank r's exchange region, as mapped in this process
+  int32_t* in[tc::MAX_PEERS];
+  float* w[tc::MAX_PEERS];
+  unsigned long long* cnt[tc::MAX_PEERS];       // rank r's arrival counter for THIS rank's results
+};
 // squared distance between two bf16 mining rows, warp-cooperative, fp32 direct differences
 __device__ __forceinline__ float xm_dist(const __nv_bfloat16* a, const __nv_bfloat16* b, int Dp, int lane) {
   float s = 0.f;
@@ -393,9 +427,10 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
                    const int32_t* __restrict__ hhead, const int32_t* __restrict__ hnext,
                    const int32_t* __restrict__ hslot, float* __restrict__ loss, int32_t* __restrict__ idx_p,
                    int32_t* __restrict__ idx_n, float* __restrict__ wgt, int32_t* __restrict__ rheadp,
-                   int32_t* __restrict__ rheadn, int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn) {
+                   int32_t* __restrict__ rheadn, int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn,
+                   const ResPush rp) {
   const long li = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (li >= B_local) return;
+  if (li < B_local) {
   const int lane = threadIdx.x & 31;
   const long gi = row_offset + li;
   int ip = -1, in = -1;
@@ -462,10 +497,8 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     ip = idx_p[li]; in = idx_n[li];
   }
   if (mode != 2 && lane == 0) { idx_p[li] = ip; idx_n[li] = in; }
-  if (ip < 0 || in < 0 || ip >= B_all || in >= B_all) {
-    if (lane == 0) { if (loss) loss[li] = 0.f; if (wgt) wgt[li] = 0.f; }
-    return;
-  }
+  float l = 0.f;
+  if (!(ip < 0 || in < 0 || ip >= B_all || in >= B_all)) {          // else: no valid triplet, loss 0, no gradient
   const T* ea = E + gi * D; const T* epp = E + (long)ip * D; const T* en = E + (long)in * D;
   // x = e * (1/|e|): one reciprocal per row instead of a division per element (<= 1 ulp from e/|e|)
   const float ra = normalize ? 1.f / nrm[gi] : 1.f, rp = normalize ? 1.f / nrm[ip] : 1.f, rn = normalize ? 1.f / nrm[in] : 1.f;
@@ -489,20 +522,28 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     }
   }
   s = warp_sum(s);
-  const float l = fmaxf(s + margin, 0.f);
+  l = fmaxf(s + margin, 0.f);
+  }
   if (lane == 0) {
     if (loss) loss[li] = l;
     // gradient bookkeeping: weight of this anchor and membership in the chains of its positive / negative row
-    float w2 = (l > 0.f) ? 2.f * (head_grad ? head_grad[li] : 1.f) : 0.f;       // relu'(0) = 0
-    if (wgt) {
-      wgt[li] = w2;
-      if (w2 != 0.f) {
-        const bool p_ok = !detach || (ip >= row_offset && ip < row_offset + B_local);
-        const bool n_ok = !detach || (in >= row_offset && in < row_offset + B_local);
-        if (p_ok) rnextp[li] = atomicExch(&rheadp[ip], (int32_t)li);
-        if (n_ok) rnextn[li] = atomicExch(&rheadn[in], (int32_t)li);
-      }
+    const float w2 = (l > 0.f) ? 2.f * (head_grad ? head_grad[li] : 1.f) : 0.f;       // relu'(0) = 0
+    if (wgt) wgt[li] = w2;
+    if (wgt && rheadp && w2 != 0.f) {
+      const bool p_ok = !detach || (ip >= row_offset && ip < row_offset + B_local);
+      const bool n_ok = !detach || (in >= row_offset && in < row_offset + B_local);
+      if (p_ok) rnextp[li] = atomicExch(&rheadp[ip], (int32_t)li);
+      if (n_ok) rnextn[li] = atomicExch(&rheadn[in], (int32_t)li);
     }
+    // multi-GPU exact gradient: this anchor's (idx_p, idx_n, weight) goes to every rank's copy of the global result
+    // arrays (plain stores over NVLink; 12 bytes per anchor per rank instead of a dense reduce-scatter of dE)
+    for (int r = 0; r < rp.world; ++r) { rp.ip[r][gi] = ip; rp.in[r][gi] = in; rp.w[r][gi] = w2; }
+  }
+  }
+  if (rp.world > 1) {                                              // one arrival per block on every peer's counter
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < rp.world && (int)threadIdx.x != rp.rank) tc::red_release_sys_add_u64(rp.cnt[threadIdx.x], 1ull);
   }
 }
 
@@ -640,6 +681,10 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
     g.M = (int)B_local; g.N = (int)B_all; g.nk = L.Dp / tc::BK;
     const int mh = tc::pick_mh(g.M, g.nk);
     const int cg = tc::pick_cg(g.M, mh, 0);
+    if (const char* e = getenv("EFM_GRAM_PHASES")) {                 // test hook: the multi-GPU block-major column schedule
+      const int ph = atoi(e), ct = (int)cdiv(B_all, 256 / mh);       // (no waits: every block is local)
+      if (ph > 1 && ct % ph == 0) { g.phases = ph; g.phase0 = (int)((row_offset * ph) / B_all) % ph; }
+    }
     const int grid = tc::plan_gram(g, mh, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, cg);
     MineEpi::Params ep{sq, lab, kneg, (int)row_offset};
     return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st, cg);
@@ -727,7 +772,7 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
     bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
                                                               B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos,
                                                               kneg, xm_bf16, L.Dp, lab, hcnt, hmem, hhead, hnext, hslot, loss, idx_p,
-                                                              idx_n, wgt, rheadp, rheadn, rnextp, rnextn);
+                                                              idx_n, wgt, rheadp, rheadn, rnextp, rnextn, ResPush{});
   });
   EFM_LAUNCH_CHECK("bh_finalize");
   if (dE_all) {
@@ -792,7 +837,7 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
                                                                 B_local, margin, head_grad, detach, 2, nullptr, nullptr, nullptr,
                                                                 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                 const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), wgt,
-                                                                rheadp, rheadn, rnextp, rnextn);
+                                                                rheadp, rheadn, rnextp, rnextn, ResPush{});
     });
     EFM_LAUNCH_CHECK("bh_finalize(bwd)");
   }
@@ -810,13 +855,20 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
 // Every rank all-gathers (idx_p, idx_n, wgt) of all anchors (12 bytes per anchor) and computes the gradient of ITS rows
 // only: the anchor-role term of its own anchors plus the positive / negative-role terms of every anchor (of any rank)
 // that picked one of its rows.  All embeddings needed are in the gathered batch already.
+// cnt != nullptr: the results of the peers' anchors are still arriving (published by their bh_finalize); every block
+// first waits until the counters of all ranks but `skip` (this rank) have reached `target`.  Loads bypass L1.
 __global__ void __launch_bounds__(256)
-bh_chain_kernel(const int32_t* __restrict__ idx_p, const int32_t* __restrict__ idx_n, const float* __restrict__ wgt,
+bh_chain_kernel(const int32_t* idx_p, const int32_t* idx_n, const float* wgt,
                 long n_anchors, long row_begin, long nrows, int32_t* __restrict__ rheadp, int32_t* __restrict__ rheadn,
-                int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn) {
+                int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn, const unsigned long long* cnt, int world,
+                int skip, unsigned long long target) {
+  if (cnt) {
+    if ((int)threadIdx.x < world && (int)threadIdx.x != skip) tc::wait_counter_thread(cnt + threadIdx.x, target);
+    __syncthreads();
+  }
   const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_anchors || wgt[j] == 0.f) return;
-  const long p = idx_p[j] - row_begin, n = idx_n[j] - row_begin;
+  if (j >= n_anchors || __ldcg(wgt + j) == 0.f) return;
+  const long p = __ldcg(idx_p + j) - row_begin, n = __ldcg(idx_n + j) - row_begin;
   if (p >= 0 && p < nrows) rnextp[j] = atomicExch(&rheadp[p], (int32_t)j);
   if (n >= 0 && n < nrows) rnextn[j] = atomicExch(&rheadn[n], (int32_t)j);
 }
@@ -867,7 +919,7 @@ extern "C" int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype
     EFM_LAUNCH_CHECK("bh_prep(stats)");
   }
   bh_chain_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(idx_p_all, idx_n_all, wgt_all, B_all, row_offset, B_local, rheadp,
-                                                                rheadn, rnextp, rnextn);
+                                                                rheadn, rnextp, rnextn, nullptr, 0, -1, 0ull);
   EFM_LAUNCH_CHECK("bh_chain");
   const unsigned grid = (unsigned)cdiv(B_local, WARPS);
   EFM_DISPATCH_DTYPE(dtype, T, {
@@ -891,4 +943,258 @@ extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long 
   EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_mine: workspace too small");
   return bh_launch_mining(L, E_all, static_cast<uint8_t*>(workspace), B_all, row_offset, B_local, D,
                           static_cast<cudaStream_t>(stream));
+}
+
+// ============================================================================================================
+// Multi-GPU step with the exchange fused into the Gram kernel (BASELINE config C3).
+//
+// One process per GPU.  Every rank owns an EXCHANGE REGION (efm_xchg_alloc: plain cudaMalloc memory, because CUDA IPC
+// cannot export sub-allocations of a caching allocator) that all peers map through CUDA IPC.  Layout (the same on
+// every rank):  [cnt_a u64[8] | cnt_b u64[8] | cnt_c u64[8] | pad to 256 B | buffer 0 | buffer 1], each buffer =
+//   xm (B_all, Dp) bf16 mining rows | sq (B_all) | lab (B_all) | nrm (B_all) | E (B_all, D) original rows |
+//   res_ip (B_all) | res_in (B_all) | res_w (B_all)
+// with rank r's rows in block r of every array.  Step s uses buffer s & 1; the counters only ever grow (step s waits for
+// s * increments-per-step), so nothing is reset between steps.  A peer can be at most one step ahead (its next Gram
+// kernel needs this rank's next push), hence two buffers suffice.
+//
+//   memset        label table + chain heads (local workspace)
+//   bh_prep       LOCAL rows only -> block `rank` of xm / sq / lab / nrm in the own region
+//   gram_kernel   <MineEpi, COMM>: a 19th warp per CTA pushes block `rank` of xm/sq/lab/nrm (stage A) and the original rows
+//                 (stage B) into every peer's region with plain stores over NVLink + one release-add per (CTA, peer,
+//                 stage) on the peer's arrival counter; the tile schedule is column-block-major starting with the
+//                 local block, and the producer / epilogue warps wait for a peer's stage-A counter right before its
+//                 first tile -> the transfer is hidden behind the tiles of the blocks that are already there
+//   bh_label_table  waits for stage B of all ranks, builds the per-label member table over the global batch
+//   bh_finalize   local anchors; exact mode: publishes (idx_p, idx_n, weight) to every rank (12 B per anchor per rank)
+//   bh_chain      exact mode: waits for the peers' results, chains of all anchors that mined a local row
+//   bh_grad       local rows only -> dE_local (B_local, D)
+// No NCCL call and no host synchronisation inside the step.
+namespace efm {
+namespace {
+
+struct XchgLayout { int Dp; size_t cnt_a, cnt_b, cnt_c, buf0, buf_bytes, xm, sq, lab, nrm, E, rip, rin, rw, total; };
+XchgLayout xchg_layout(long B, int world, long D, int dtype) {
+  XchgLayout L{};
+  L.Dp = (int)(cdiv(D, tc::BK) * tc::BK);
+  const size_t B_all = (size_t)B * world;
+  L.cnt_a = 0; L.cnt_b = 64; L.cnt_c = 128; L.buf0 = 256;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.xm = take(B_all * L.Dp * 2);
+  L.sq = take(B_all * 4); L.lab = take(B_all * 4); L.nrm = take(B_all * 4);
+  L.E = take(B_all * D * dtype_size(dtype));
+  L.rip = take(B_all * 4); L.rin = take(B_all * 4); L.rw = take(B_all * 4);
+  L.buf_bytes = off;
+  L.total = L.buf0 + 2 * L.buf_bytes;
+  return L;
+}
+
+struct DistLayout { int tbits; size_t kpos, kneg, hkeys, hcnt, hhead, rheadp, rheadn, clr_begin, clr_bytes, hmem, hnext, hslot, rnextp, rnextn, wgt, total; };
+DistLayout dist_layout(long B, long B_all) {
+  DistLayout L{};
+  L.tbits = 4;
+  while ((1L << L.tbits) < 2 * B_all) ++L.tbits;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.kpos = take((size_t)B * 8); L.kneg = take((size_t)B * 8);
+  L.hkeys = take((size_t)8 << L.tbits); L.hcnt = take((size_t)4 << L.tbits); L.hhead = take((size_t)4 << L.tbits);
+  L.rheadp = take((size_t)B_all * 4); L.rheadn = take((size_t)B_all * 4);
+  L.clr_begin = L.hkeys; L.clr_bytes = off - L.clr_begin;
+  L.hmem = take((size_t)32 << L.tbits);
+  L.hnext = take((size_t)B_all * 4); L.hslot = take((size_t)B_all * 4);
+  L.rnextp = take((size_t)B_all * 4); L.rnextn = take((size_t)B_all * 4);
+  L.wgt = take((size_t)B * 4);
+  L.total = off;
+  return L;
+}
+
+int dist_check_shape(const char* who, long B, int world, int rank, long D, int dtype) {
+  EFM_REQUIRE(world >= 1 && world <= tc::MAX_PEERS && rank >= 0 && rank < world, EFM_E_ARG, "%s: world=%d rank=%d (at most %d ranks)",
+              who, world, rank, tc::MAX_PEERS);
+  EFM_REQUIRE(B > 0 && D > 0, EFM_E_ARG, "%s: bad shape B_local=%ld D=%ld", who, B, D);
+  EFM_REQUIRE(dtype == EFM_F32 || dtype == EFM_BF16 || dtype == EFM_F16, EFM_E_ARG, "%s: dtype %d", who, dtype);
+  EFM_REQUIRE(B % 256 == 0, EFM_E_UNSUPPORTED, "%s: B_local=%ld must be a multiple of 256 (whole 256-column tile blocks per rank)", who, B);
+  EFM_REQUIRE(D % 8 == 0 && cdiv(D, tc::BK) <= tc::MAX_NK, EFM_E_UNSUPPORTED, "%s: D=%ld must be a multiple of 8 and <= %d", who, D,
+              tc::MAX_NK * tc::BK);
+  EFM_REQUIRE((long)B * world < (1L << 30), EFM_E_ARG, "%s: global batch too large", who);
+  return EFM_OK;
+}
+
+}  // namespace
+}  // namespace efm
+
+extern "C" size_t efm_bh_xchg_bytes(long B_local, int world, long D, int dtype) {
+  if (B_local <= 0 || world < 1 || world > tc::MAX_PEERS || D <= 0) return 0;
+  return xchg_layout(B_local, world, D, dtype).total;
+}
+extern "C" size_t efm_bh_dist_workspace_bytes(long B_local, int world) {
+  if (B_local <= 0 || world < 1) return 0;
+  return dist_layout(B_local, B_local * world).total;
+}
+
+extern "C" int efm_xchg_alloc(size_t bytes, void** region) {
+  EFM_REQUIRE(region && bytes > 0, EFM_E_ARG, "efm_xchg_alloc: bad argument");
+  void* p = nullptr;
+  EFM_CUDA(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);                              // arrival counters start at 0
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "efm_xchg_alloc: memset"); }
+  *region = p;
+  return EFM_OK;
+}
+extern "C" int efm_xchg_free(void* region) {
+  if (region) EFM_CUDA(cudaFree(region));
+  return EFM_OK;
+}
+extern "C" int efm_ipc_export(const void* region, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  EFM_REQUIRE(region && handle64, EFM_E_ARG, "efm_ipc_export: null pointer");
+  cudaIpcMemHandle_t h;
+  EFM_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(region)));
+  memcpy(handle64, &h, sizeof(h));
+  return EFM_OK;
+}
+extern "C" int efm_ipc_import(const void* handle64, void** mapped) {
+  EFM_REQUIRE(handle64 && mapped, EFM_E_ARG, "efm_ipc_import: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  EFM_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *mapped = p;
+  return EFM_OK;
+}
+extern "C" int efm_ipc_release(void* mapped) {
+  if (mapped) EFM_CUDA(cudaIpcCloseMemHandle(mapped));
+  return EFM_OK;
+}
+
+static thread_local cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+extern "C" int efm_bh_profile_events(void* ev_start, void* ev_end) {
+  g_prof_ev[0] = static_cast<cudaEvent_t>(ev_start);
+  g_prof_ev[1] = static_cast<cudaEvent_t>(ev_end);
+  return EFM_OK;
+}
+
+extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_local, long B_local, long D, int dtype,
+                                   float margin, const float* head_grad, int flags, int world, int rank,
+                                   void* const* regions, unsigned long long step, float* loss, int32_t* idx_p,
+                                   int32_t* idx_n, float* dE_local, void* workspace, size_t ws_bytes, void* stream) {
+  { const int rc = dist_check_shape("efm_bh_dist_fwd_bwd", B_local, world, rank, D, dtype); if (rc) return rc; }
+  EFM_REQUIRE(E_local && labels_local && regions && loss && idx_p && idx_n && workspace, EFM_E_ARG, "efm_bh_dist_fwd_bwd: null pointer");
+  EFM_REQUIRE(step >= 1, EFM_E_ARG, "efm_bh_dist_fwd_bwd: step counts from 1 (the same value on every rank)");
+  EFM_REQUIRE(aligned(workspace, 256) && aligned(E_local, 16) && (!dE_local || aligned(dE_local, 16)), EFM_E_ALIGN,
+              "efm_bh_dist_fwd_bwd: workspace must be 256-byte, E_local / dE_local 16-byte aligned");
+  for (int r = 0; r < world; ++r) EFM_REQUIRE(regions[r] && aligned(regions[r], 256), EFM_E_ARG, "efm_bh_dist_fwd_bwd: region %d missing", r);
+  const long B = B_local, B_all = B * world, row0 = B * rank;
+  const XchgLayout X = xchg_layout(B, world, D, dtype);
+  const DistLayout L = dist_layout(B, B_all);
+  EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_dist_fwd_bwd: workspace %zu < required %zu", ws_bytes, L.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint8_t* own = static_cast<uint8_t*>(regions[rank]);
+  const size_t boff = X.buf0 + (size_t)(step & 1ull) * X.buf_bytes;      // this step's buffer inside every region
+  uint8_t* buf = own + boff;
+  auto* xm = reinterpret_cast<__nv_bfloat16*>(buf + X.xm);
+  float* sq = reinterpret_cast<float*>(buf + X.sq);
+  int32_t* lab = reinterpret_cast<int32_t*>(buf + X.lab);
+  float* nrm = reinterpret_cast<float*>(buf + X.nrm);
+  const void* E_all = buf + X.E;
+  int32_t* rip = reinterpret_cast<int32_t*>(buf + X.rip);
+  int32_t* rin = reinterpret_cast<int32_t*>(buf + X.rin);
+  float* rw = reinterpret_cast<float*>(buf + X.rw);
+  auto* kpos = reinterpret_cast<unsigned long long*>(ws + L.kpos);
+  auto* kneg = reinterpret_cast<unsigned long long*>(ws + L.kneg);
+  auto* hkeys = reinterpret_cast<unsigned long long*>(ws + L.hkeys);
+  int32_t* hcnt = reinterpret_cast<int32_t*>(ws + L.hcnt);
+  int32_t* hmem = reinterpret_cast<int32_t*>(ws + L.hmem);
+  int32_t* hhead = reinterpret_cast<int32_t*>(ws + L.hhead);
+  int32_t* hnext = reinterpret_cast<int32_t*>(ws + L.hnext);
+  int32_t* hslot = reinterpret_cast<int32_t*>(ws + L.hslot);
+  int32_t* rheadp = reinterpret_cast<int32_t*>(ws + L.rheadp);
+  int32_t* rheadn = reinterpret_cast<int32_t*>(ws + L.rheadn);
+  int32_t* rnextp = reinterpret_cast<int32_t*>(ws + L.rnextp);
+  int32_t* rnextn = reinterpret_cast<int32_t*>(ws + L.rnextn);
+  float* wgt = reinterpret_cast<float*>(ws + L.wgt);
+  const int normalize = (flags & EFM_BH_NORMALIZE) ? 1 : 0;
+  const bool exact = dE_local && !(flags & EFM_BH_DETACH_GATHERED);
+  const size_t es = dtype_size(dtype);
+  const unsigned grid_loc = (unsigned)(B / WARPS);
+
+  EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));
+  // 1. local rows -> block `rank` of this step's buffer
+  EFM_DISPATCH_DTYPE(dtype, T, {
+    bh_prep_kernel<T, true><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_local, labels_local, B, (int)D, X.Dp, normalize, 1, 0, 0, B,
+                                                             sq + row0, nrm + row0, lab + row0, xm + row0 * X.Dp, nullptr, kpos, kneg,
+                                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  });
+  EFM_LAUNCH_CHECK("bh_prep(local)");
+  // 2. Gram + mining + exchange
+  unsigned long long target_ab = 0;
+  {
+    tc::GramParams g{};
+    g.M = (int)B; g.N = (int)B_all; g.nk = X.Dp / tc::BK;
+    g.phases = world; g.phase0 = rank;
+    const int grid = tc::plan_gram(g, 1, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, 2);
+    EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "efm_bh_dist_fwd_bwd: D = %ld leaves no shared memory for the B pipeline", D);
+    target_ab = step * (unsigned long long)grid;                         // every CTA of a sender adds 1 per (peer, stage) per step
+    g.ready = reinterpret_cast<const unsigned long long*>(own + X.cnt_a);
+    g.ready_target = target_ab;
+    tc::CommParams cp{};
+    cp.world = world; cp.rank = rank; cp.nseg_a = 4; cp.nseg = 5; cp.self_b = 1;
+    for (int r = 0; r < world; ++r) cp.peer[r] = static_cast<uint8_t*>(regions[r]);
+    cp.seg[0] = {reinterpret_cast<const uint8_t*>(xm + row0 * X.Dp), boff + X.xm + (size_t)row0 * X.Dp * 2, (unsigned long long)B * X.Dp * 2};
+    cp.seg[1] = {reinterpret_cast<const uint8_t*>(sq + row0), boff + X.sq + (size_t)row0 * 4, (unsigned long long)B * 4};
+    cp.seg[2] = {reinterpret_cast<const uint8_t*>(lab + row0), boff + X.lab + (size_t)row0 * 4, (unsigned long long)B * 4};
+    cp.seg[3] = {reinterpret_cast<const uint8_t*>(nrm + row0), boff + X.nrm + (size_t)row0 * 4, (unsigned long long)B * 4};
+    cp.seg[4] = {static_cast<const uint8_t*>(E_local), boff + X.E + (size_t)row0 * D * es, (unsigned long long)B * D * es};
+    cp.cnt_a_off = X.cnt_a; cp.cnt_b_off = X.cnt_b;
+    MineEpi::Params ep{sq, lab, kneg, (int)row0};
+    if (g_prof_ev[0]) EFM_CUDA(cudaEventRecord(g_prof_ev[0], st));
+    const int rc = tc::launch_gram_mh<MineEpi, 1, 2, true>(xm + row0 * X.Dp, xm, g, ep, grid, st, &cp);
+    if (rc) return rc;
+    if (g_prof_ev[1]) EFM_CUDA(cudaEventRecord(g_prof_ev[1], st));
+  }
+  // 3. label table over the global batch (waits for stage B: the original rows of every rank, own copy included)
+  bh_label_table_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(lab, B_all, hkeys, hcnt, hmem, hhead, hnext, hslot, L.tbits,
+                                                                     reinterpret_cast<const unsigned long long*>(own + X.cnt_b), world,
+                                                                     target_ab);
+  EFM_LAUNCH_CHECK("bh_label_table");
+  // 4. finalize the local anchors
+  ResPush rp{};
+  {                                                                      // published in every mode, so the result counters of all
+    rp.world = world; rp.rank = rank;                                    // ranks advance in lockstep whatever mix of flags is used
+    for (int r = 0; r < world; ++r) {
+      uint8_t* b = static_cast<uint8_t*>(regions[r]) + boff;
+      rp.ip[r] = reinterpret_cast<int32_t*>(b + X.rip); rp.in[r] = reinterpret_cast<int32_t*>(b + X.rin);
+      rp.w[r] = reinterpret_cast<float*>(b + X.rw);
+      rp.cnt[r] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(regions[r]) + X.cnt_c) + rank;
+    }
+  }
+  const bool chains_local = dE_local && !exact;
+  EFM_DISPATCH_DTYPE(dtype, T, {
+    bh_finalize_kernel<T, true><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row0, B, margin, head_grad,
+                                                                 chains_local ? 1 : 0, 1, kpos, kneg, xm, X.Dp, lab, hcnt, hmem, hhead,
+                                                                 hnext, hslot, loss, idx_p, idx_n, chains_local ? wgt : nullptr,
+                                                                 chains_local ? rheadp : nullptr, rheadn, rnextp, rnextn, rp);
+  });
+  EFM_LAUNCH_CHECK("bh_finalize(dist)");
+  if (!dE_local) return EFM_OK;
+  // 5./6. gradient of the local rows
+  if (exact) {
+    bh_chain_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(rip, rin, rw, B_all, row0, B, rheadp, rheadn, rnextp, rnextn,
+                                                                  reinterpret_cast<const unsigned long long*>(own + X.cnt_c), world, rank,
+                                                                  step * (unsigned long long)grid_loc);
+    EFM_LAUNCH_CHECK("bh_chain(dist)");
+    EFM_DISPATCH_DTYPE(dtype, T, {
+      bh_grad_kernel<T, 8><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B, (int)D, 0, B_all, rip, rin, rw, rheadp,
+                                                            rheadn, rnextp, rnextn, dE_local, row0);
+    });
+  } else {
+    EFM_DISPATCH_DTYPE(dtype, T, {
+      bh_grad_kernel<T, 8><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B, (int)D, row0, B, idx_p, idx_n, wgt,
+                                                            rheadp + row0, rheadn + row0, rnextp, rnextn, dE_local, row0);
+    });
+  }
+  EFM_LAUNCH_CHECK("bh_grad(dist)");
+  return EFM_OK;
 }

@@ -54,6 +54,32 @@ struct GramParams {
   int row_blocks, col_tiles;
   int sched_mode;        // 0: contiguous tile ranges over the whole grid; 1: `splits` CTAs per row block
   int splits;
+  // Column blocks ("phases", multi-GPU mining): the N columns are `phases` equal blocks, one per rank, visited
+  // block-major starting at block `phase0` (the local rank's rows, already resident).  Before the first tile of any
+  // other block the kernel waits until that block's arrival counter (incremented by the owning peer's pushes over
+  // NVLink, see CommParams) has reached `ready_target`.  phases = 1: one block, no waits.
+  int phases, phase0;
+  const unsigned long long* ready;       // [phases] arrival counters in LOCAL memory; nullptr = nothing to wait for
+  unsigned long long ready_target;
+};
+
+// ---- peer exchange fused into the Gram kernel (one process per GPU, peers mapped through CUDA IPC) -------------
+// Every rank owns an exchange region with the same layout.  A rank's kernel PUSHES its own rows into the same offsets
+// of every peer's region with plain stores over NVLink (posted writes; nobody ever reads remote memory), stage A (what
+// the peers' mining needs: bf16 mining rows, |x|^2, labels, norms) before stage B (the original rows, needed only after
+// mining), destinations ordered by when the receiver's block-major schedule reaches this rank's block.  After the share
+// of one CTA for one destination: fence.sys, then one release-add on the destination's arrival counter for this rank.
+constexpr int MAX_PEERS = 8;
+constexpr int MAX_PUSH_SEGS = 6;
+struct PushSeg { const uint8_t* src; unsigned long long dst_off; unsigned long long bytes; };   // 16-byte multiples
+struct CommParams {
+  int world, rank;
+  int nseg_a, nseg;                      // segments [0, nseg_a): stage A, [nseg_a, nseg): stage B
+  int self_b;                            // stage B is also copied into this rank's OWN region (last), so that the
+                                         // gathered rows are contiguous locally without a separate copy
+  uint8_t* peer[MAX_PEERS];              // base of rank r's exchange region as mapped in this process (peer[rank] = own)
+  PushSeg seg[MAX_PUSH_SEGS];
+  unsigned long long cnt_a_off, cnt_b_off;   // offsets of the u64[world] arrival counters inside a region
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
@@ -152,8 +178,73 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
+// ---- cross-GPU helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_sys_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+static __device__ __noinline__ void peer_timeout(const void* p, unsigned long long have, unsigned long long want) {
+  printf("efmtl: peer wait timeout block %d thread %d counter %p = %llu < %llu\n", blockIdx.x, threadIdx.x, p, have, want);
+  __trap();
+}
+// One thread polls (acquire, system scope) with back-off.  Bounded: a lost peer traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_counter_thread(const unsigned long long* p, unsigned long long target) {
+  unsigned long long v = ld_acquire_sys_u64(p);
+  if (v < target) {
+    const unsigned long long t0 = gtimer();
+    while ((v = ld_acquire_sys_u64(p)) < target) {
+      __nanosleep(200);
+      if (gtimer() - t0 > 8000000000ull) peer_timeout(p, v, target);         // 8 s
+    }
+  }
+}
+// Whole warp calls; lane 0 polls, the rest of the warp is ordered behind it by the warp barrier.
+__device__ __forceinline__ void wait_counter(const unsigned long long* p, unsigned long long target) {
+  if ((threadIdx.x & 31) == 0) wait_counter_thread(p, target);
+  __syncwarp();
+}
+// one warp copies its CTA's share of a segment: 16-byte units, 8 loads in flight per lane, plain (posted) stores
+__device__ __forceinline__ void push_share(uint8_t* dst, const uint8_t* src, unsigned long long bytes, int part, int nparts, int lane) {
+  const long U = (long)(bytes >> 4);
+  const long lo = U * part / nparts, hi = U * (part + 1) / nparts;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  long u = lo + lane;
+  for (; u + 7 * 32 < hi; u += 8 * 32) {
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = s4[u + k * 32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d4[u + k * 32] = v[k];
+  }
+  for (; u < hi; u += 32) d4[u] = s4[u];
+}
+// the push of one CTA (`part` of `nparts`), executed by one warp
+__device__ __forceinline__ void comm_push(const CommParams& cp, int part, int nparts) {
+  const int lane = threadIdx.x & 31;
+  for (int stage = 0; stage < 2; ++stage) {
+    const int s0 = stage ? cp.nseg_a : 0, s1 = stage ? cp.nseg : cp.nseg_a;
+    if (s0 == s1) continue;
+    const int last = (stage && cp.self_b) ? cp.world : cp.world - 1; // ph = world: this rank's own region
+    for (int ph = 1; ph <= last; ++ph) {
+      int dest = cp.rank - ph; if (dest < 0) dest += cp.world;       // the receiver that reaches this rank's block at phase ph
+      uint8_t* base = cp.peer[dest];
+      for (int s = s0; s < s1; ++s) push_share(base + cp.seg[s].dst_off, cp.seg[s].src, cp.seg[s].bytes, part, nparts, lane);
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0)
+        red_release_sys_add_u64(reinterpret_cast<unsigned long long*>(base + (stage ? cp.cnt_b_off : cp.cnt_a_off)) + cp.rank, 1ull);
+    }
+  }
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -246,20 +337,56 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 // ---- tile schedule -------------------------------------------------------------------------------------
+// Tiles are visited phase by phase (one phase = one column block; a single phase unless the columns come from several
+// ranks).  Inside a phase a CTA (pair) owns a contiguous range of the phase's tiles in row-major order, so its A row
+// block stays resident while it walks column tiles.  All three roles (TMA, MMA, epilogue) run the same iterator.
 template <int CG>
-__device__ __forceinline__ void tile_range(const GramParams& g, long& t0, long& t1) {
-  const long CT = g.col_tiles;
-  if (g.sched_mode == 0) {
-    const long T = (long)g.row_blocks * CT, G = gridDim.x / CG, c = blockIdx.x / CG;   // CG = 2: one range per CTA pair
-    t0 = c * T / G;
-    t1 = (c + 1) * T / G;
-  } else {
-    const long c = blockIdx.x / CG;
-    const long rb = c / g.splits, s = c % g.splits;
-    t0 = rb * CT + s * CT / g.splits;
-    t1 = rb * CT + (s + 1) * CT / g.splits;
+struct TileIter {
+  int CTp, phases, phase0;   // column tiles per phase
+  int sched_mode, splits, row_blocks;
+  int ph, left;              // current phase; tiles left in it after the current one
+  int rb, ctl, ct0;          // row block; column tile inside the phase's block; first column tile of that block
+  bool new_rb, new_phase;
+  __device__ __forceinline__ explicit TileIter(const GramParams& g)
+      : CTp(g.col_tiles / g.phases), phases(g.phases), phase0(g.phase0), sched_mode(g.sched_mode), splits(g.splits),
+        row_blocks(g.row_blocks), ph(-1), left(0), rb(0), ctl(0), ct0(0), new_rb(false), new_phase(false) {}
+  __device__ __forceinline__ void range(long& t0, long& t1) const {
+    const long CT = CTp;
+    if (sched_mode == 0) {
+      const long T = (long)row_blocks * CT, G = gridDim.x / CG, c = blockIdx.x / CG;   // CG = 2: one range per CTA pair
+      t0 = c * T / G;
+      t1 = (c + 1) * T / G;
+    } else {                                                         // `splits` CTAs (pairs) per row block; single phase
+      const long c = blockIdx.x / CG;
+      const long r = c / splits, s = c % splits;
+      t0 = r * CT + s * CT / splits;
+      t1 = r * CT + (s + 1) * CT / splits;
+    }
   }
-}
+  __device__ __forceinline__ bool next() {
+    if (left > 0) {
+      --left;
+      new_phase = false;
+      if (++ctl == CTp) { ctl = 0; ++rb; new_rb = true; } else new_rb = false;
+      return true;
+    }
+    while (++ph < phases) {
+      long t0, t1;
+      range(t0, t1);                                                 // the only divisions: once per phase
+      if (t1 > t0) {
+        left = (int)(t1 - t0) - 1;
+        rb = (int)(t0 / CTp); ctl = (int)(t0 % CTp);
+        int blk = phase0 + ph; if (blk >= phases) blk -= phases;
+        ct0 = blk * CTp;
+        new_rb = new_phase = true;
+        return true;
+      }
+    }
+    return false;
+  }
+  __device__ __forceinline__ int ct() const { return ct0 + ctl; }    // global column tile
+  __device__ __forceinline__ int block() const { return ct0 / CTp; }
+};
 
 template <int MH> inline size_t smem_bytes(int nk, int stages, int extra) {
   return 1024 /*alignment slack*/ + (size_t)nk * Shape<MH>::A_KB_BYTES + (size_t)stages * Shape<MH>::B_ST_BYTES + 256 /*barriers*/ + extra;
@@ -286,10 +413,11 @@ template <int MH> inline int pick_stages(int nk, int extra) {
 // which reads both halves, so every SM pulls half the B bytes from L2 and reads half the B bytes from shared memory per
 // MAC.  Barriers: full / a_full / acc_empty live in the leader (TMA of both CTAs credits the leader, the peer's epilogue
 // arrives remotely); empty / a_empty / acc_full are signalled in both CTAs by multicast tcgen05.commit.
-template <class Epi, int MH, int CG>
-__global__ void __launch_bounds__(THREADS, 1)
+// COMM: a 19th warp pushes this rank's rows to the peers' exchange regions while the tiles run (see CommParams).
+template <class Epi, int MH, int CG, bool COMM>
+__global__ void __launch_bounds__(THREADS + (COMM ? 32 : 0), 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams g,
-            const typename Epi::Params ep) {
+            const typename Epi::Params ep, const CommParams cp) {
   static_assert(CG == 1 || MH == 1, "the 2-CTA path uses the 128 x 256 per-CTA shape");
   constexpr int BM = Shape<MH>::BM, BN = Shape<MH>::BN;              // per-CTA accumulator tile
   constexpr int A_KB_BYTES = Shape<MH>::A_KB_BYTES, B_ST_BYTES = Shape<MH>::B_ST_BYTES / CG;   // CG = 2: half a B stage per CTA
@@ -311,7 +439,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t bar_acc_empty = bar_acc_full + 16;     // [2]
   const uint32_t tmem_slot = bar_acc_empty + 16;        // u32
   float* scratch = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw))) +
-                   (threadIdx.x >> 5) * (Epi::SMEM_PER_WARP / 4);   // epilogue warps are warps 0..7
+                   ((threadIdx.x >> 5) & (EPI_WARPS - 1)) * (Epi::SMEM_PER_WARP / 4);   // epilogue warps are warps 0..15
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -337,20 +465,20 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) EFM_TRACE(1);
 
-  long t0l, t1l;
-  tile_range<CG>(g, t0l, t1l);
-  const int CT = g.col_tiles;
-  const int ntiles = (int)(t1l - t0l);
-  const int rb0 = (int)(t0l / CT), ct0 = (int)(t0l % CT);           // the only divisions; tiles advance incrementally
-
   if (warp == PRODUCER_WARP) {
     // whole warp runs the (warp-uniform) loop so counters live in uniform registers; one elected lane issues
     const uint32_t leader = elect_one();
     int stage = 0; uint32_t phase = 0, a_empty_phase = 0;
-    int rb = rb0, ct = ct0;
-    for (int i = 0; i < ntiles; ++i) {
-      if (i == 0 || ct == 0) {                                       // new row block: (re)load the resident A block
-        if (i != 0) { mbar_wait(bar_a_empty, a_empty_phase); a_empty_phase ^= 1; }
+    TileIter<CG> it(g);
+    bool first = true;
+    while (it.next()) {
+      const int rb = it.rb, ct = it.ct();
+      if (it.new_phase && it.ph > 0 && g.ready) {                    // a peer's column block: wait until it has landed
+        wait_counter(g.ready + it.block(), g.ready_target);
+        fence_proxy_async_all();                                     // remote generic-proxy writes -> our TMA (async proxy) reads
+      }
+      if (it.new_rb) {                                               // new row block: (re)load the resident A block
+        if (!first) { mbar_wait(bar_a_empty, a_empty_phase); a_empty_phase ^= 1; }
         if (leader) {
           if constexpr (CG == 2) {
             if (crank == 0) mbar_expect_tx(bar_a_full, (uint32_t)g.nk * A_KB_BYTES * 2);      // both CTAs' A blocks
@@ -376,18 +504,21 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
-      if (i == 0) EFM_TRACE(2);
-      if (++ct == CT) { ct = 0; ++rb; }
+      if (first) EFM_TRACE(2);
+      first = false;
     }
   } else if (warp == MMA_WARP && crank == 0) {
     const uint32_t leader = elect_one();
     int stage = 0; uint32_t phase = 0, a_full_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    int ct = ct0;
     const uint64_t descA0 = smem_desc(sA), descB0 = smem_desc(sB);
-    for (int i = 0; i < ntiles; ++i) {
+    TileIter<CG> nx(g);
+    bool has = nx.next();
+    while (has) {
+      const bool new_rb = nx.new_rb;
+      has = nx.next();                                               // nx now describes the tile after this one
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);             // epilogue drained this accumulator
-      if (i == 0 || ct == 0) { mbar_wait(bar_a_full, a_full_phase); a_full_phase ^= 1; }
+      if (new_rb) { mbar_wait(bar_a_full, a_full_phase); a_full_phase ^= 1; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
       for (int kb = 0; kb < g.nk; ++kb) {
@@ -414,7 +545,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
-      const bool last_of_rb = (i + 1 == ntiles) || (ct + 1 == CT);
+      const bool last_of_rb = !has || nx.new_rb;
       if (leader) {
         if constexpr (CG == 2) {
           umma_commit_2cta(bar_acc_full + 8 * acc);
@@ -424,8 +555,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (last_of_rb) umma_commit(bar_a_empty);                  // A row-block may be overwritten
         }
       }
-      if (i + 1 == ntiles) EFM_TRACE(5);
-      if (++ct == CT) ct = 0;
+      if (!has) EFM_TRACE(5);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp < EPI_WARPS) {
@@ -439,18 +569,26 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int row = 0;
     const int part = cs;
     constexpr int CW = Epi::CW;                                      // columns per TMEM load / epilogue chunk
-    int rb = rb0, ct = ct0;
-    if (ntiles > 0) Epi::prefetch(ep, g, scratch, 0, ct0 * BN + cs * COLS_PER_WARP);
-    for (int i = 0; i < ntiles; ++i) {
-      if (i == 0 || ct == 0) {
+    TileIter<CG> nx(g);
+    bool has = nx.next();
+    if (has) {
+      if (nx.ph > 0 && g.ready) wait_counter(g.ready + nx.block(), g.ready_target);   // no tile in the local block
+      Epi::prefetch(ep, g, scratch, 0, nx.ct() * BN + cs * COLS_PER_WARP);
+    }
+    int i = 0;
+    while (has) {
+      if (nx.new_rb) {
         if (i != 0) Epi::row_end(ep, g, row, part, st);
-        row = (rb * CG + (int)crank) * BM + rowhalf * 128 + quarter * 32 + lane;
+        row = (nx.rb * CG + (int)crank) * BM + rowhalf * 128 + quarter * 32 + lane;
         Epi::row_begin(ep, g, row, st);
       }
-      const int colw = ct * BN + cs * COLS_PER_WARP;                 // first column of this warp's slice
+      const int colw = nx.ct() * BN + cs * COLS_PER_WARP;            // first column of this warp's slice
+      has = nx.next();                                               // nx now describes the tile after this one
       Epi::prefetch_wait();                                          // this tile's per-column data has landed
-      if (i + 1 < ntiles)                                            // next tile's data: in flight during this tile
-        Epi::prefetch(ep, g, scratch, (i + 1) & 1, (ct + 1 == CT ? 0 : ct + 1) * BN + cs * COLS_PER_WARP);
+      if (has) {                                                     // next tile's data: in flight during this tile
+        if (nx.new_phase && g.ready) wait_counter(g.ready + nx.block(), g.ready_target);   // ... once its block has arrived
+        Epi::prefetch(ep, g, scratch, (i + 1) & 1, nx.ct() * BN + cs * COLS_PER_WARP);
+      }
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
       if (i == 0 && warp == 0) EFM_TRACE(3);
@@ -473,11 +611,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (CG == 2) mbar_arrive_cluster(bar_acc_empty + 8 * acc, 0);   // the leader's MMA thread waits for both CTAs
         else mbar_arrive(bar_acc_empty + 8 * acc);
       }
-      if (warp == 0) { if (i == 0) EFM_TRACE(4); if (i + 1 == ntiles) EFM_TRACE(6); }
+      if (warp == 0) { if (i == 0) EFM_TRACE(4); if (!has) EFM_TRACE(6); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (++ct == CT) { ct = 0; ++rb; }
+      ++i;
     }
-    if (ntiles > 0) Epi::row_end(ep, g, row, part, st);
+    if (i > 0) Epi::row_end(ep, g, row, part, st);
+  } else if (COMM && warp == MMA_WARP + 1) {
+    if (cp.world > 1 || cp.self_b) comm_push(cp, (int)blockIdx.x, (int)gridDim.x);
   }
 
   tc_fence_before();
@@ -494,31 +634,36 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // 2-D bf16 row-major (rows, Kp) tensor map with a (64 x box_rows) box, SWIZZLE_128B, zero OOB fill.
 int make_tmap_bf16(CUtensorMap* out, const void* base, long rows, long Kp, int box_rows);
 
-template <class Epi, int MH, int CG>
-int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Epi::Params& ep, int grid, cudaStream_t st) {
+template <class Epi, int MH, int CG, bool COMM = false>
+int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Epi::Params& ep, int grid, cudaStream_t st,
+                   const CommParams* cp = nullptr) {
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, 128);       // A box: 128 rows per TMA (MH = 2 issues it per 256-row block)
   if (MH == 2) rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, Shape<MH>::BM);
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, B, g.N, (long)g.nk * BK, Shape<MH>::BN / CG);
   if (rc) return rc;
+  if (g.phases < 1) g.phases = 1;
   const size_t smem = 1024 + (size_t)g.nk * Shape<MH>::A_KB_BYTES + (size_t)g.stages * (Shape<MH>::B_ST_BYTES / CG) + 256 +
                       Epi::SMEM_PER_WARP * EPI_WARPS;
   static bool attr_done = false;                                     // per instantiation
   if (!attr_done) {
-    EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi, MH, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi, MH, CG, COMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
+  CommParams none{};
+  const CommParams& c = cp ? *cp : none;
+  constexpr unsigned NT = THREADS + (COMM ? 32 : 0);
   if (CG == 2) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    EFM_CUDA(cudaLaunchKernelEx(&cfg, gram_kernel<Epi, MH, CG>, tmA, tmB, g, ep));
+    EFM_CUDA(cudaLaunchKernelEx(&cfg, gram_kernel<Epi, MH, CG, COMM>, tmA, tmB, g, ep, c));
   } else {
-    gram_kernel<Epi, MH, CG><<<grid, THREADS, smem, st>>>(tmA, tmB, g, ep);
+    gram_kernel<Epi, MH, CG, COMM><<<grid, NT, smem, st>>>(tmA, tmB, g, ep, c);
   }
   EFM_LAUNCH_CHECK("gram_kernel");
   return EFM_OK;
@@ -558,7 +703,8 @@ inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0, 
     }
     if (forced && forced < g.stages) g.stages = forced; }
   g.sched_mode = sched_mode;
-  const long T = (long)g.row_blocks * g.col_tiles;
+  if (g.phases < 1) g.phases = 1;                                    // caller sets phases > 1 (col_tiles % phases == 0, mode 0)
+  const long T = (long)g.row_blocks * (g.col_tiles / g.phases);      // tiles of one phase: every CTA (pair) takes a share of each
   const int sms = num_sms();
   if (sched_mode == 0) {
     g.splits = 1;

@@ -7,7 +7,8 @@
  *
  * Conventions (all entry points)
  *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; the library
- *     never allocates, frees or synchronises; work is enqueued on `stream` (a cudaStream_t passed
+ *     never allocates, frees or synchronises (one exception: the IPC exchange regions of the multi-GPU
+ *     step, efm_xchg_alloc / efm_xchg_free); work is enqueued on `stream` (a cudaStream_t passed
  *     as void*, NULL = legacy default stream);
  *   - return 0 on success, <0 on error (EFM_E_*); efm_last_error() returns a thread-local message
  *     (mirrors the reference's return -1 / false convention, Feature.hpp:215-217,314-317);
@@ -138,6 +139,41 @@ size_t efm_bh_grad_rows_workspace_bytes(long B_all, long B_local);
 int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype, int flags, const int32_t* idx_p_all,
                      const int32_t* idx_n_all, const float* wgt_all, long row_offset, long B_local,
                      float* dE_local, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- multi-GPU global batch-hard step with the exchange fused into the Gram kernel (BASELINE config C3) ----
+ * Replaces the data-parallel split of mutli_gpu_v3.py:153 for the loss head: one process per GPU, rank r owns B_local
+ * rows; the global batch is world * B_local rows, rank r's rows are global rows [r*B_local, (r+1)*B_local).
+ *
+ * Exchange regions: every rank allocates one with efm_xchg_alloc(efm_bh_xchg_bytes(...)) -- plain cudaMalloc memory,
+ * zero-filled; the ONE place where the library allocates, because CUDA IPC cannot export sub-allocations of a caching
+ * allocator -- exports it with efm_ipc_export (64-byte handle, sent to the peers by any host channel) and maps every
+ * peer's region with efm_ipc_import.  `regions[r]` (HOST array of `world` device pointers) is rank r's region as
+ * mapped in this process, regions[rank] the own allocation.  All ranks must have mapped all regions before the first
+ * step and must call efm_bh_dist_fwd_bwd with the same shapes, flags and `step` (1, 2, 3, ... -- it selects one of two
+ * buffers and the value the arrival counters are compared with; nothing is reset between steps).
+ *
+ * The step enqueues prep (local rows) -> Gram + mining kernel that also PUSHES this rank's rows into every peer's
+ * region over NVLink and waits, column block by column block, for the peers' rows (see csrc/bh.cu) -> label table ->
+ * finalize (exact mode publishes 12 bytes per anchor to every rank) -> gradient of the local rows.  No NCCL call, no
+ * host synchronisation.  Results equal efm_bh_triplet_fwd_bwd on the concatenated batch: loss / idx_p / idx_n
+ * (B_local; indices are global rows), dE_local (B_local, D) fp32 or NULL (forward only).  EFM_BH_DETACH_GATHERED:
+ * gradient only through roles played by local rows of local anchors (no result exchange).  Mining always runs on the
+ * tcgen05 path (bf16-rounded rows).  Requires B_local % 256 == 0, D % 8 == 0, D <= 512, world <= 8.
+ * A peer that never arrives makes the waiting kernel trap after 8 s (launch failure) instead of hanging. */
+size_t efm_bh_xchg_bytes(long B_local, int world, long D, int dtype);
+size_t efm_bh_dist_workspace_bytes(long B_local, int world);
+int efm_xchg_alloc(size_t bytes, void** region);
+int efm_xchg_free(void* region);
+int efm_ipc_export(const void* region, void* handle64 /* 64 bytes, host */);
+int efm_ipc_import(const void* handle64, void** mapped);
+int efm_ipc_release(void* mapped);
+int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_local, long B_local, long D, int dtype,
+                        float margin, const float* head_grad, int flags, int world, int rank,
+                        void* const* regions, unsigned long long step, float* loss, int32_t* idx_p,
+                        int32_t* idx_n, float* dE_local, void* workspace, size_t ws_bytes, void* stream);
+/* Profiling aid: the next efm_bh_dist_fwd_bwd calls of this thread record these cudaEvent_t (passed as void*) right
+ * before / after the Gram + mining + exchange kernel on the call's stream; (NULL, NULL) switches it off. */
+int efm_bh_profile_events(void* ev_start, void* ev_end);
 
 /* ---- a8-a11: gallery scoring ---------------------------------------------------------------------
  * simd_dot (Feature.hpp:273-293) + Compare_Face_From_DB (:345-392 argmax, :295-343 top-K) +

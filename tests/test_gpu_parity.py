@@ -328,6 +328,68 @@ def test_bh_row_sliced_gradient_equals_full(P, dtype):
     assert rel_err(torch.cat(parts).cpu().numpy(), ref["dE_all"]) < (1e-4 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("phases", [2, 4])
+def test_bh_block_major_column_schedule(P, phases, monkeypatch):
+    """The multi-GPU tile schedule (column blocks visited block-major, starting at the anchors' own block) mines the same
+    triplets as the plain row-major schedule.  EFM_GRAM_PHASES is the single-GPU test hook for it."""
+    E, y = clustered(2048, 256, seed=41)
+    Et, yt = dev(E, torch.bfloat16), dev(y)
+    full = P.batch_hard_triplet(Et, yt, 1.9)
+    monkeypatch.setenv("EFM_GRAM_PHASES", str(phases))
+    for r in range(2):
+        l, ip, inn, _ = P.batch_hard_triplet(Et, yt, 1.9, row_offset=r * 1024, num_local=1024)
+        assert torch.equal(ip, full[1][r * 1024:(r + 1) * 1024]) and torch.equal(inn, full[2][r * 1024:(r + 1) * 1024])
+        assert torch.equal(l, full[0][r * 1024:(r + 1) * 1024])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("exact", [True, False])
+def test_bh_fused_exchange_step_world1(P, dtype, exact):
+    """efm_bh_dist_fwd_bwd with a single rank (the exchange kernel copies the rows into the rank's own region, the
+    arrival counters gate the later kernels): same mined triplets, loss and gradient as the single-GPU fused call,
+    over several steps (both buffers of the region are used)."""
+    from improving_face_recognition_performance_using_triplet_loss_b200.distributed import PeerExchange
+    B, D = 512, 128
+    px = PeerExchange(B, D, dtype)
+    try:
+        for s in range(3):
+            E, y = clustered(B, D, seed=50 + s)
+            Et, yt = dev(E, dtype), dev(y)
+            ref = P.batch_hard_triplet(Et, yt, 1.9, mine_bf16=True)
+            hg = torch.linspace(0.5, 1.5, B).cuda() if s == 2 else None
+            if hg is not None:
+                ref = P.batch_hard_triplet(Et, yt, 1.9, mine_bf16=True, head_grad=hg)
+            l, ip, inn, dE = px.step(Et, yt, 1.9, exact_grad=exact, head_grad=hg)
+            assert (ref[0] > 0).sum() > 64
+            assert torch.equal(ip, ref[1]) and torch.equal(inn, ref[2])
+            assert torch.equal(l, ref[0])
+            assert rel_err(dE.cpu().numpy(), ref[3].cpu().numpy()) < 1e-5
+    finally:
+        px.close()
+
+
+def test_bh_fused_exchange_rejects_bad_shapes(P):
+    from improving_face_recognition_performance_using_triplet_loss_b200.distributed import PeerExchange
+    with pytest.raises(ValueError):
+        PeerExchange(200, 128, torch.bfloat16)
+    with pytest.raises(ValueError):
+        PeerExchange(256, 1024, torch.bfloat16)
+
+
+def test_bh_fused_exchange_two_gpus():
+    """The real thing: 2 ranks under torchrun, exchange over NVLink peer memory (skipped on a single-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(here, "dist_gpu_check.py"), "--B", "512", "--steps", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_bh_autograd_module(P):
     E, y = clustered(256, 64, seed=5)
     for red in ("none", "sum", "mean"):
