@@ -6,9 +6,15 @@
 Metric (BASELINE.json): triplet-loss fwd+bwd embeddings/sec.
 Workload at N=1: BASELINE config C2 -- batch-hard triplet loss forward+backward, B=8192 x D=256 bf16
 embeddings (2048 identities x 4), margin 0.2, per-row L2 normalisation with backward, on one B200.
-N>1: every rank keeps B_local=8192 anchors and mines them against the all-gathered global batch
-(8192*N rows; N=8 is BASELINE config C3, 65,536 x 256): NCCL all-gather forward, reduce-scatter of dE
-backward.  A "step" is one pass of that path over one batch of synthetic embeddings.
+N>1: BASELINE config C3 -- global batch 65,536 x 256 (16,384 identities x 4) split over the N GPUs
+(65,536/N anchors per rank mined against the whole global batch; "strong" scaling: total work fixed).
+The step is the FUSED multi-GPU step (efm_bh_dist_fwd_bwd): no NCCL call -- the Gram + mining kernel pushes
+the rank's rows into the peers' exchange regions over NVLink while it mines the blocks that have already
+arrived; exact gradient (12 bytes per anchor published to every rank, no dense reduce-scatter).  The line
+also carries `c3_single_gpu_ms_per_step` (the same 65,536-row job on rank 0 alone, measured in the same run)
+and `speedup_vs_single_gpu`.  `--workload c3-nccl` runs the NCCL all-gather form, `--workload c3-weak`
+8192 anchors per GPU against the all-gathered batch.  A "step" is one pass of that path over one batch of
+synthetic embeddings.
 
 One JSON line on rank 0 (see the contract in the task statement): value = whole-job embeddings/s with
 inputs resident in HBM (per-step CUDA events, L2 flushed between steps), e2e = same through the public
@@ -117,18 +123,40 @@ def time_cpu(E, y, budget_s=25.0, max_steps=5):
     return best, n
 
 
+def workload_of(args, world):
+    """-> (name, global batch G, scaling label)"""
+    w = args.workload
+    if w == "auto":
+        w = "c2" if world == 1 else "c3"
+    if w == "c2":
+        return "c2", B_LOCAL * world, "weak"
+    if w == "c3-weak":
+        return "c3-weak", B_LOCAL * world, "weak"
+    if w in ("c3", "c3-nccl", "c3-strong"):
+        return ("c3-nccl" if w == "c3-nccl" else "c3"), 65536, "strong"
+    raise SystemExit("unknown workload %s" % w)
+
+
+def workload_label(name, world, G):
+    if name == "c2":
+        return "C2 batch-hard triplet fwd+bwd B=8192 D=256"
+    if name == "c3-weak":
+        return "C3-style global batch-hard mining: 8192 anchors/GPU vs all-gathered %dx256" % G
+    return "C3 global batch-hard triplet fwd+bwd: global batch 65536x256 over %d GPU%s" % (world, "" if world == 1 else "s")
+
+
 def run_reference(args):
     """--impl reference: the reference path's CPU arithmetic on all host cores (oracle port: numpy + BLAS; MXNet is
     not installable and no reference implementation of batch-hard mining exists -- see DESIGN.md).  Same workload as
-    our arm at this N (global batch 8192*N); every step processes a BOUNDED SAMPLE of it: a strip of 8192/N anchors
-    mined against the whole global batch (the same 67 M pairs at every N), value = anchors of the strip / time."""
+    our arm at this N; every step processes a BOUNDED SAMPLE of it: a strip of S anchors mined against the whole global
+    batch, value = anchors of the strip / time."""
     import oracle as O
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     world = max(1, args.gpus)
-    G = B_LOCAL * world
-    S = max(64, B_LOCAL // world)
+    name, G, scaling = workload_of(args, world)
+    S = max(64, B_LOCAL // world) if name != "c3" and name != "c3-nccl" else 1024
     E, y = make_batch(G, DIM, 0)
     cores = os.cpu_count() or 1
 
@@ -147,11 +175,9 @@ def run_reference(args):
     val = S / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("C2 batch-hard triplet fwd+bwd B=8192 D=256" if world == 1 else
-                                "C3-style global batch-hard mining: 8192 anchors/GPU vs all-gathered %dx256" % G),
-                   "B_global": G, "D": DIM, "margin": MARGIN, "normalize": True},
+        "config": {"workload": workload_label(name, world, G), "B_global": G, "D": DIM, "margin": MARGIN, "normalize": True},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "strip of %d anchors x %d-row global batch per step (numpy fp32: normalise, sgemm Gram strip, "
                                    "argmax/argmin, hinge, scatter, normalise-backward)" % (S, G)},
@@ -178,8 +204,7 @@ def run_ours(args):
     from improving_face_recognition_performance_using_triplet_loss_b200 import _lib as L
     from improving_face_recognition_performance_using_triplet_loss_b200 import distributed as D
 
-    strong = args.workload == "c3-strong"
-    G = 65536 if strong else B_LOCAL * world
+    name, G, scaling = workload_of(args, world)
     B = G // world
     E_np, y_np = make_batch(G, DIM, 0)
     lo = rank * B
@@ -191,25 +216,52 @@ def run_ours(args):
 
     flags = L.BH_NORMALIZE
     dt = L.BF16
-    ws = L.workspace(L.lib.efm_bh_workspace_bytes(B, G, DIM, dt, flags), dev)
     loss = torch.empty(B, dtype=torch.float32, device=dev)
     idx_p = torch.empty(B, dtype=torch.int32, device=dev)
     idx_n = torch.empty(B, dtype=torch.int32, device=dev)
-    dE_all = torch.empty((G, DIM), dtype=torch.float32, device=dev)
-    dE_loc = torch.empty((B, DIM), dtype=torch.float32, device=dev) if world > 1 else dE_all
-    E_all = torch.empty((G, DIM), dtype=torch.bfloat16, device=dev) if world > 1 else E_loc
-    y_all = torch.empty(G, dtype=torch.int32, device=dev) if world > 1 else y_loc
 
-    def step():
-        """One pass of the hot path over one batch, inputs resident in HBM."""
-        if world > 1:
-            dist.all_gather_into_tensor(E_all, E_loc)
-            dist.all_gather_into_tensor(y_all, y_loc)
-        L.check(L.lib.efm_bh_triplet_fwd_bwd(L.ptr(E_all), L.ptr(y_all), G, lo, B, DIM, dt, MARGIN, None, flags,
-                                             L.ptr(loss), L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE_all), L.ptr(ws), ws.numel(),
-                                             L.stream()))
-        if world > 1:
-            dist.reduce_scatter_tensor(dE_loc, dE_all)
+    # ---- the step of this workload
+    px = None
+    fused = world > 1 and name == "c3"
+    if fused:
+        try:
+            px = D.PeerExchange(B, DIM, torch.bfloat16, device=dev)
+        except Exception as e:  # noqa: BLE001  (no peer access / IPC on this box: say so and use the NCCL form)
+            if rank == 0:
+                print("bench: fused exchange unavailable (%s); using the NCCL all-gather form" % e, file=sys.stderr, flush=True)
+            fused = False
+        ok = torch.tensor([1 if fused else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok) and px is not None:
+            px.close(); px = None
+        fused = bool(int(ok))
+    if fused:
+        dE_loc = torch.empty((B, DIM), dtype=torch.float32, device=dev)
+        launches_per_step = ["bh_prep", "gram_kernel<MineEpi,COMM>", "bh_finalize", "bh_chain", "bh_grad"]
+
+        def step():
+            px.steps += 1
+            L.check(L.lib.efm_bh_dist_fwd_bwd(L.ptr(E_loc), L.ptr(y_loc), B, DIM, dt, MARGIN, None, flags, world, rank, px.regions,
+                                              px.steps, L.ptr(loss), L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE_loc), L.ptr(px.ws),
+                                              px.ws.numel(), L.stream()))
+    else:
+        ws = L.workspace(L.lib.efm_bh_workspace_bytes(B, G, DIM, dt, flags), dev)
+        dE_all = torch.empty((G, DIM), dtype=torch.float32, device=dev)
+        dE_loc = torch.empty((B, DIM), dtype=torch.float32, device=dev) if world > 1 else dE_all
+        E_all = torch.empty((G, DIM), dtype=torch.bfloat16, device=dev) if world > 1 else E_loc
+        y_all = torch.empty(G, dtype=torch.int32, device=dev) if world > 1 else y_loc
+        launches_per_step = ["bh_prep", "gram_kernel<MineEpi>", "bh_finalize", "bh_grad"]
+
+        def step():
+            """One pass of the hot path over one batch, inputs resident in HBM."""
+            if world > 1:
+                dist.all_gather_into_tensor(E_all, E_loc)
+                dist.all_gather_into_tensor(y_all, y_loc)
+            L.check(L.lib.efm_bh_triplet_fwd_bwd(L.ptr(E_all), L.ptr(y_all), G, lo, B, DIM, dt, MARGIN, None, flags,
+                                                 L.ptr(loss), L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE_all), L.ptr(ws), ws.numel(),
+                                                 L.stream()))
+            if world > 1:
+                dist.reduce_scatter_tensor(dE_loc, dE_all)
 
     def barrier():
         if world > 1:
@@ -231,29 +283,59 @@ def run_ours(args):
     barrier()
     ms = [s.elapsed_time(e) for s, e in evs]
     t_step = float(np.sum(ms)) / args.steps
-    # ---- dominant kernel alone (tcgen05 Gram + mining).  A ~30 us kernel timed launch-by-launch carries ~4-6 us of
-    # launch + event latency that is not kernel time (ncu gpu__time_duration of the same launch: 31-33 us), so each event
-    # pair brackets KREP back-to-back launches (L2 flushed before every group; the 4.2 MB of inputs are re-read from L2
-    # by the later launches of a group exactly as they are inside the step, where bh_prep has just written them).
     KREP = 5
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s, e in kev:
+    # ---- per-kernel breakdown of the step: the library records an event at every stage boundary (efm_bh_profile_events)
+    import ctypes as C
+    stage_ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+    for ev in stage_ev:
+        ev.record(stream)                                              # creates the underlying cudaEvent_t handles
+    torch.cuda.synchronize()
+    ev_arr = (C.c_void_p * 7)(*[ev.cuda_event for ev in stage_ev])
+    names = ["memset+prep", "gram+mining" + ("+exchange+label_table" if fused else ""), "-", "finalize", "chain", "grad"]
+    acc = np.zeros(6); nb = min(args.steps, 20)
+    L.check(L.lib.efm_bh_profile_events(ev_arr, 7))
+    for _ in range(nb):
         flush.zero_()
-        s.record(stream)
-        for _ in range(KREP):
+        if world > 1:
+            dist.barrier()
+        step()
+        torch.cuda.synchronize()
+        bounds = [0, 1, 2, 2, 4, 5, 6] if fused else [0, 1, 2, 2, 4, 4, 6]
+        for k in range(6):
+            a, b = bounds[k], bounds[k + 1]
+            if a != b:
+                acc[k] += stage_ev[a].elapsed_time(stage_ev[b])
+    L.check(L.lib.efm_bh_profile_events(None, 0))
+    barrier()
+    breakdown = {names[k]: round(1e3 * acc[k] / nb, 2) for k in range(6) if acc[k] > 0}
+    if fused:
+        # dominant kernel = the fused Gram + mining + exchange kernel, timed INSIDE the step (it cannot run alone: it waits
+        # for the peers' pushes)
+        t_kernel = t_kernel_single = float(acc[1] / nb)
+        KREP = 1
+    else:
+        # ---- dominant kernel alone (tcgen05 Gram + mining).  A ~30 us kernel timed launch-by-launch carries ~4-6 us of
+        # launch + event latency that is not kernel time (ncu gpu__time_duration of the same launch: 31-33 us), so each event
+        # pair brackets KREP back-to-back launches (L2 flushed before every group; the 4.2 MB of inputs are re-read from L2
+        # by the later launches of a group exactly as they are inside the step, where bh_prep has just written them).
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for s, e in kev:
+            flush.zero_()
+            s.record(stream)
+            for _ in range(KREP):
+                L.check(L.lib.efm_bh_mine(L.ptr(E_all), G, lo, B, DIM, dt, flags, L.ptr(ws), ws.numel(), L.stream()))
+            e.record(stream)
+        barrier()
+        t_kernel = float(np.mean([s.elapsed_time(e) for s, e in kev])) / KREP
+        # single launches (flush before each) for reference
+        kev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 20))]
+        for s, e in kev1:
+            flush.zero_()
+            s.record(stream)
             L.check(L.lib.efm_bh_mine(L.ptr(E_all), G, lo, B, DIM, dt, flags, L.ptr(ws), ws.numel(), L.stream()))
-        e.record(stream)
-    barrier()
-    t_kernel = float(np.mean([s.elapsed_time(e) for s, e in kev])) / KREP
-    # single launches (flush before each) for reference
-    kev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 20))]
-    for s, e in kev1:
-        flush.zero_()
-        s.record(stream)
-        L.check(L.lib.efm_bh_mine(L.ptr(E_all), G, lo, B, DIM, dt, flags, L.ptr(ws), ws.numel(), L.stream()))
-        e.record(stream)
-    barrier()
-    t_kernel_single = float(np.mean([s.elapsed_time(e) for s, e in kev1]))
+            e.record(stream)
+        barrier()
+        t_kernel_single = float(np.mean([s.elapsed_time(e) for s, e in kev1]))
     clocks = sampler.stop()
 
     # ---- e2e: public API, pinned host buffers in, loss + indices out, every step (wall clock)
@@ -263,13 +345,16 @@ def run_ours(args):
 
     def e2e_step():
         Ed = E_host.to(dev, non_blocking=True); yd = y_host.to(dev, non_blocking=True)
-        if world > 1:
-            Ea = D.all_gather_rows(Ed); ya = D.all_gather_rows(yd)
+        if fused:
+            l, ip, inn, dE = px.step(Ed, yd, MARGIN, normalize=True)
         else:
-            Ea, ya = Ed, yd
-        l, ip, inn, dE = P.batch_hard_triplet(Ea, ya, MARGIN, normalize=True, row_offset=lo, num_local=B, workspace=ws)
-        if world > 1:
-            dist.reduce_scatter_tensor(dE_loc, dE)
+            if world > 1:
+                Ea = D.all_gather_rows(Ed); ya = D.all_gather_rows(yd)
+            else:
+                Ea, ya = Ed, yd
+            l, ip, inn, dE = P.batch_hard_triplet(Ea, ya, MARGIN, normalize=True, row_offset=lo, num_local=B, workspace=ws)
+            if world > 1:
+                dist.reduce_scatter_tensor(dE_loc, dE)
         loss_h.copy_(l, non_blocking=True); ip_h.copy_(ip, non_blocking=True); in_h.copy_(inn, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -282,6 +367,36 @@ def run_ours(args):
     barrier()
     t_e2e = (time.perf_counter() - t0) / args.steps
 
+    # ---- C3 on N > 1 GPUs: the same 65,536-row job on ONE GPU (rank 0 alone), for the speed-up the north star asks for
+    t_single = None
+    if world > 1 and scaling == "strong":
+        if px is not None:
+            px.close(); px = None
+        if rank == 0 and not args.no_single:
+            Eg = torch.from_numpy(E_np).to(torch.bfloat16).to(dev); yg = torch.from_numpy(y_np).to(dev)
+            ws1 = L.workspace(L.lib.efm_bh_workspace_bytes(G, G, DIM, dt, flags), dev)
+            l1 = torch.empty(G, dtype=torch.float32, device=dev)
+            p1 = torch.empty(G, dtype=torch.int32, device=dev); n1 = torch.empty(G, dtype=torch.int32, device=dev)
+            d1 = torch.empty((G, DIM), dtype=torch.float32, device=dev)
+
+            def single():
+                L.check(L.lib.efm_bh_triplet_fwd_bwd(L.ptr(Eg), L.ptr(yg), G, 0, G, DIM, dt, MARGIN, None, flags, L.ptr(l1), L.ptr(p1),
+                                                     L.ptr(n1), L.ptr(d1), L.ptr(ws1), ws1.numel(), L.stream()))
+            for _ in range(3):
+                single()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(min(args.steps, 10)):
+                flush.zero_()
+                s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+                s0.record(stream); single(); s1.record(stream)
+                torch.cuda.synchronize()
+                ts.append(s0.elapsed_time(s1))
+            t_single = float(np.mean(ts))
+        dist.barrier()
+    elif px is not None:
+        px.close(); px = None
+
     # ---- max over ranks
     if world > 1:
         t = torch.tensor([t_step, t_kernel, t_e2e * 1e3, t_kernel_single], dtype=torch.float64, device=dev)
@@ -293,37 +408,49 @@ def run_ours(args):
         flops = 2.0 * B * G * DIM                                      # full Gram strip, symmetry not credited
         traffic = None                                                 # dram bytes of one launch, from the committed ncu capture
         tf = os.path.join(ROOT, "profiles", "r1_gram_final_summary.json")
-        if world == 1 and not strong and os.path.exists(tf):
+        if world == 1 and name == "c2" and os.path.exists(tf):
             with open(tf) as f:
                 traffic = json.load(f).get("traffic_bytes_per_launch")
         achieved = flops / (t_kernel * 1e-3) / 1e12
         peak = float(pk["bf16_tflops"])                                # burst figure: kernel timed alone
+        if fused:
+            par = "dp%d, exchange fused into the Gram kernel over NVLink peer memory (no NCCL); exact gradient via 12 B/anchor" % world
+            kname = "gram_kernel<MineEpi,COMM> (tcgen05 Gram + mining epilogue + NVLink push/arrival waits), timed inside the step"
+        elif world > 1:
+            par = "dp%d NCCL all-gather fwd / reduce-scatter bwd" % world
+            kname = "gram_kernel<MineEpi> (tcgen05 Gram + batch-hard mining epilogue)"
+        else:
+            par = "single GPU"
+            kname = "gram_kernel<MineEpi> (tcgen05 Gram + batch-hard mining epilogue)"
         line = {
             "metric": METRIC, "value": G / (t_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_step, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": ("C3-strong global 65536x256" if strong else
-                             ("C2 batch-hard triplet fwd+bwd B=8192 D=256" if world == 1 else
-                              "C3-style global batch-hard mining: 8192 anchors/GPU vs all-gathered %dx256" % G)),
+                "workload": workload_label(name, world, G),
                 "B_local": B, "B_global": G, "D": DIM, "ids_per": IDS_PER, "margin": MARGIN, "normalize": True,
-                "parallelism": "dp%d all-gather fwd / reduce-scatter bwd" % world if world > 1 else "single GPU",
+                "parallelism": par,
                 "l2": "256 MiB buffer zeroed between steps, outside the per-step CUDA events",
                 "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks",
             },
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "gram_kernel<MineEpi> (tcgen05 Gram + batch-hard mining epilogue)",
+                         "traffic": traffic, "kernel": kname,
                          "kernel_ms": t_kernel, "kernel_ms_single_launch": t_kernel_single, "launches_per_event_pair": KREP,
                          "flops_per_launch": flops, "peak_source": pk_src + ", burst bf16"},
             "e2e": {"value": G / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(E_host.numel() * 2 + y_host.numel() * 4),
                     "d2h_bytes_per_step": int(B * 12), "ms_per_step": t_e2e * 1e3,
-                    "how": "public API batch_hard_triplet(), pinned host E+labels -> device, loss+idx_p+idx_n -> pinned host, "
-                           "stream sync every step, wall clock"},
-            "gpu_launches": 4 * args.steps,   # kernels of the timed steps (the roofline / e2e loops launch theirs on top) "launches_per_step": ["bh_prep", "gram_kernel<MineEpi>", "bh_finalize", "bh_grad"], "memsets_per_step": 1,
+                    "how": "public API (%s), pinned host E+labels -> device, loss+idx_p+idx_n -> pinned host, "
+                           "stream sync every step, wall clock" % ("PeerExchange.step()" if fused else "batch_hard_triplet()")},
+            "gpu_launches": len(launches_per_step) * args.steps,   # kernels of the timed steps (the roofline / e2e loops launch theirs on top)
+            "launches_per_step": launches_per_step, "memsets_per_step": 1,
+            "step_breakdown_us": breakdown,   # CUDA events between the launches of one step (each interval includes its launch gap)
             "clocks": clocks,
             "pairs_per_s": (float(B) * G * world) / (t_step * 1e-3),
         }
-        if world == 1 and not args.no_cpu:
+        if t_single is not None:
+            line["c3_single_gpu_ms_per_step"] = t_single
+            line["speedup_vs_single_gpu"] = t_single / t_step
+        if world == 1 and name == "c2" and not args.no_cpu:
             best, n = time_cpu(E_np, y_np)
             line["cpu_baseline"] = {"value": B / best, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "full C2 batch, best of %d steps (oracle numpy/BLAS port: Gram + mining + hinge "
@@ -339,8 +466,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3-strong"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c3-strong", "c3-nccl", "c3-weak"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same C3 job")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -76,43 +76,6 @@ template <typename T> __device__ __forceinline__ void load8(const T* p, float (&
   }
 }
 
-// ------------------------------------------------------------------------------------------ per-label member table
-// register `row` with its label: open-addressing table of 64-bit tags; the first 8 members of a label are stored
-// inline (no pointer chasing in bh_finalize), further members go to an overflow chain
-__device__ __forceinline__ void label_table_insert(int32_t lab, long row, unsigned long long* __restrict__ hkeys,
-                                                   int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem,
-                                                   int32_t* __restrict__ hhead, int32_t* __restrict__ hnext,
-                                                   int32_t* __restrict__ hslot, int tbits) {
-  const unsigned long long tag = (unsigned long long)(uint32_t)lab;     // upper half 0: never equals EMPTY (~0)
-  const uint32_t mask = (1u << tbits) - 1u;
-  uint32_t sl = ((uint32_t)lab * 2654435761u) >> (32 - tbits);
-  for (;;) {
-    const unsigned long long old = atomicCAS(&hkeys[sl], ~0ull, tag);
-    if (old == ~0ull || old == tag) break;
-    sl = (sl + 1) & mask;
-  }
-  hslot[row] = (int32_t)sl;
-  const int pos = atomicAdd(&hcnt[sl], 1) + 1;                       // counter starts at -1
-  if (pos < 8) hmem[sl * 8 + pos] = (int32_t)row;
-  else hnext[row] = atomicExch(&hhead[sl], (int32_t)row);
-}
-
-// Multi-GPU step: the labels of the peers' rows arrive during the Gram kernel, so the table is built afterwards, one
-// thread per row.  Every block first waits until all `world` arrival counters (stage B of the exchange: the original
-// rows bh_finalize reads next) have reached `target`; stream order then covers the kernels that follow.
-__global__ void __launch_bounds__(256)
-bh_label_table_kernel(const int32_t* __restrict__ lab, long B_all, unsigned long long* __restrict__ hkeys,
-                      int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem, int32_t* __restrict__ hhead,
-                      int32_t* __restrict__ hnext, int32_t* __restrict__ hslot, int tbits,
-                      const unsigned long long* __restrict__ cnt, int world, unsigned long long target) {
-  if (cnt) {
-    if ((int)threadIdx.x < world) tc::wait_counter_thread(cnt + threadIdx.x, target);
-    __syncthreads();
-  }
-  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row < B_all) label_table_insert(lab[row], row, hkeys, hcnt, hmem, hhead, hnext, hslot, tbits);
-}
-
 // ------------------------------------------------------------------------------------------ prep
 // One warp per row of E_all.  VEC8: D % 8 == 0 and 16-byte aligned rows -> each lane owns 8-element slabs.
 template <typename T, bool VEC8>
@@ -124,6 +87,7 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
                unsigned long long* __restrict__ kneg, float* __restrict__ dE,
                unsigned long long* __restrict__ hkeys, int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem,
                int32_t* __restrict__ hhead, int32_t* __restrict__ hnext, int32_t* __restrict__ hslot, int tbits) {
+  pdl_trigger();                                    // the Gram kernel's prologue may overlap this kernel's tail
   const long row = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= B_all) return;
   const int lane = threadIdx.x & 31;
@@ -236,7 +200,7 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
     }
     const long li = row - row_offset;
     if (kpos && li >= 0 && li < B_local) { kpos[li] = KEY_POS_EMPTY; kneg[li] = KEY_NEG_EMPTY; }
-    if (hkeys) label_table_insert(lab, row, hkeys, hcnt, hmem, hhead, hnext, hslot, tbits);
+    if (hkeys) tc::label_table_insert(lab, row, hkeys, hcnt, hmem, hhead, hnext, hslot, tbits);
   }
 }
 
@@ -393,13 +357,15 @@ bh_mine_f32_kernel(const float* __restrict__ X, const float* __restrict__ sq, co
 }
 
 // ------------------------------------------------------------------------------------------ finalize
-// Multi-GPU exact gradient (see efm_bh_dist_fwd_bwd): where bh_finalize publishes an anchor's mining result.
-struct ResPush {
-  int world, rank;                              // world = 0: nothing to publish
-  int32_t* ip[tc::MAX_PEERS];                   // (B_all) arrays inside rank r's exchange region, as mapped in this process
-  int32_t* in[tc::MAX_PEERS];
-  float* w[tc::MAX_PEERS];
-  unsigned long long* cnt[tc::MAX_PEERS];       // rank r's arrival counter for THIS rank's results
+// Multi-GPU step (see efm_bh_dist_fwd_bwd): what bh_finalize waits for, where it publishes an anchor's mining result and
+// whom it tells.  Results stay in LOCAL memory (this rank's exchange region, where the peers' chain kernels read them over
+// NVLink): the only remote traffic of the kernel is one release-add per block on every peer's arrival counter.
+struct DistFin {
+  int world, rank;                              // world = 0: single-GPU call, nothing of this applies
+  const unsigned long long* wait_b;             // [world] local arrival counters of exchange stage B (the original rows read below)
+  unsigned long long target_b;
+  int32_t* rip; int32_t* rin; float* rw;        // (B_all) result arrays of this step in the own region, indexed by global row
+  unsigned long long* sig[tc::MAX_PEERS];       // rank r's arrival counter for THIS rank's results
 };
 // squared distance between two bf16 mining rows, warp-cooperative, fp32 direct differences
 __device__ __forceinline__ float xm_dist(const __nv_bfloat16* a, const __nv_bfloat16* b, int Dp, int lane) {
@@ -428,7 +394,13 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
                    const int32_t* __restrict__ hslot, float* __restrict__ loss, int32_t* __restrict__ idx_p,
                    int32_t* __restrict__ idx_n, float* __restrict__ wgt, int32_t* __restrict__ rheadp,
                    int32_t* __restrict__ rheadn, int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn,
-                   const ResPush rp) {
+                   const DistFin df) {
+  pdl_trigger();
+  pdl_wait();                                                        // the mining kernel has completed
+  if (df.world > 1) {                                                // the peers' original rows must have landed
+    if ((int)threadIdx.x < df.world) tc::wait_counter_thread(df.wait_b + threadIdx.x, df.target_b);
+    __syncthreads();
+  }
   const long li = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (li < B_local) {
   const int lane = threadIdx.x & 31;
@@ -445,12 +417,18 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     const __nv_bfloat16* xi = xm + gi * Dp;
     const int my = lab[gi];
     const int sl = hslot[gi];
-    const int cnt = hcnt[sl] + 1;
     const unsigned long long kn = kneg[li];
     const int g0 = (kn == KEY_NEG_EMPTY) ? -1 : (int)(uint32_t)(kn & 0xffffffffull);
+    // second round trip: member count, inline members (read unconditionally, masked by the count afterwards) and the
+    // labels of the group's columns all depend on the first one only
     int mine = -1;                                                   // lane l < 8: member l; lanes 8-11: group column
-    if (lane < 8) { if (lane < cnt) mine = hmem[sl * 8 + lane]; if (mine == gi) mine = -1; }
-    else if (lane < 12 && g0 >= 0) { const int c = g0 + lane - 8; if (c < B_all && lab[c] != my) mine = c; }
+    int clab = my;
+    const int c = g0 + lane - 8;
+    if (lane < 8) mine = hmem[sl * 8 + lane];
+    else if (lane < 12 && g0 >= 0 && c < B_all) clab = lab[c];
+    const int cnt = hcnt[sl] + 1;
+    if (lane < 8) { if (lane >= cnt || mine == gi) mine = -1; }
+    else if (clab != my) mine = c;
     const unsigned vmask = __ballot_sync(0xffffffffu, mine >= 0);
     const int ncand = __popc(vmask);
     int lanes_per = ncand <= 2 ? 16 : (ncand <= 4 ? 8 : (ncand <= 8 ? 4 : 2));
@@ -535,15 +513,17 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
       if (p_ok) rnextp[li] = atomicExch(&rheadp[ip], (int32_t)li);
       if (n_ok) rnextn[li] = atomicExch(&rheadn[in], (int32_t)li);
     }
-    // multi-GPU exact gradient: this anchor's (idx_p, idx_n, weight) goes to every rank's copy of the global result
-    // arrays (plain stores over NVLink; 12 bytes per anchor per rank instead of a dense reduce-scatter of dE)
-    for (int r = 0; r < rp.world; ++r) { rp.ip[r][gi] = ip; rp.in[r][gi] = in; rp.w[r][gi] = w2; }
+    // multi-GPU exact gradient: (idx_p, idx_n, weight) of every anchor is what the other ranks need from this one
+    // (12 bytes per anchor instead of a dense reduce-scatter of dE); they fetch it from here once this block has signalled
+    if (df.world > 0) { df.rip[gi] = ip; df.rin[gi] = in; df.rw[gi] = w2; }
   }
   }
-  if (rp.world > 1) {                                              // one arrival per block on every peer's counter
-    __threadfence_system();
+  if (df.world > 1) {                                              // one arrival per block on every peer's counter
+    __threadfence();
     __syncthreads();
-    if ((int)threadIdx.x < rp.world && (int)threadIdx.x != rp.rank) tc::red_release_sys_add_u64(rp.cnt[threadIdx.x], 1ull);
+#pragma unroll
+    for (int r = 0; r < tc::MAX_PEERS; ++r)                       // static indices: the parameter array stays in constant memory
+      if ((int)threadIdx.x == r && r < df.world && r != df.rank) tc::red_release_sys_add_u64(df.sig[r], 1ull);
   }
 }
 
@@ -574,6 +554,7 @@ bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int norma
                const float* __restrict__ wgt, const int32_t* __restrict__ rheadp, const int32_t* __restrict__ rheadn,
                const int32_t* __restrict__ rnextp, const int32_t* __restrict__ rnextn, float* __restrict__ dE,
                long row_begin) {
+  pdl_wait();
   // rows [row_begin, row_begin + B_all) are processed (B_all = number of output rows); anchors are rows
   // [row_offset, row_offset + B_local) and index idx_p / idx_n / wgt / rnext*; rhead* and dE are indexed by the
   // processed row (r - row_begin).  Fused single-call form: row_begin = 0, B_all = all rows.  Row-sliced form
@@ -668,8 +649,24 @@ bh_grad_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int norma
 
 using namespace efm;
 
+// Profiling aid: stage-boundary events of the batch-hard step (see efm_bh_profile_events in efmtl.h).
+// Boundary i is recorded after: 0 nothing (step start), 1 memset + prep, 2 Gram + mining (+ exchange), 3 (unused),
+// 4 finalize, 5 chains (multi-GPU exact gradient only), 6 gradient.
+static thread_local cudaEvent_t g_prof_ev[EFM_BH_PROFILE_EVENTS] = {};
+static thread_local int g_prof_n = 0;
+extern "C" int efm_bh_profile_events(void* const* events, int n) {
+  EFM_REQUIRE(n >= 0 && n <= EFM_BH_PROFILE_EVENTS && (n == 0 || events), EFM_E_ARG, "efm_bh_profile_events: n=%d", n);
+  for (int i = 0; i < n; ++i) g_prof_ev[i] = static_cast<cudaEvent_t>(events[i]);
+  g_prof_n = n;
+  return EFM_OK;
+}
+#define EFM_BH_STAGE(i, st)                                                            \
+  do {                                                                                 \
+    if ((i) < g_prof_n && g_prof_ev[i]) EFM_CUDA(cudaEventRecord(g_prof_ev[i], (st))); \
+  } while (0)
+
 static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, long B_all, long row_offset, long B_local,
-                            long D, cudaStream_t st) {
+                            long D, cudaStream_t st, bool pdl = false) {
   auto* kpos = reinterpret_cast<unsigned long long*>(ws + L.kpos);
   auto* kneg = reinterpret_cast<unsigned long long*>(ws + L.kneg);
   float* sq = reinterpret_cast<float*>(ws + L.sq);
@@ -687,7 +684,7 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
     }
     const int grid = tc::plan_gram(g, mh, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, cg);
     MineEpi::Params ep{sq, lab, kneg, (int)row_offset};
-    return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st, cg);
+    return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st, cg, pdl);
   }
   const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
   const int row_blocks = (int)cdiv(B_local, FM);
@@ -756,6 +753,7 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   const unsigned grid_all = (unsigned)cdiv(B_all, WARPS), grid_loc = (unsigned)cdiv(B_local, WARPS);
   const bool vec = bh_vec8(E_all, D, dE_all);
 
+  EFM_BH_STAGE(0, st);
   EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));     // empty label table + empty chains
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, labels_all, B_all, (int)D, L.Dp, normalize,
@@ -764,25 +762,28 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
                                                           hhead, hnext, hslot, L.tbits);
   });
   EFM_LAUNCH_CHECK("bh_prep");
+  EFM_BH_STAGE(1, st);
   {
-    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, st);
+    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, st, true);
     if (rc) return rc;
   }
+  EFM_BH_STAGE(2, st);
   EFM_BH_DISPATCH(dtype, vec, T, V, {
-    bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                              B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos,
-                                                              kneg, xm_bf16, L.Dp, lab, hcnt, hmem, hhead, hnext, hslot, loss, idx_p,
-                                                              idx_n, wgt, rheadp, rheadn, rnextp, rnextn, ResPush{});
+    EFM_LAUNCH((bh_finalize_kernel<T, V>), grid_loc, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
+               B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos, kneg, xm_bf16, L.Dp, lab, hcnt, hmem, hhead, hnext, hslot,
+               loss, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, DistFin{});
   });
   EFM_LAUNCH_CHECK("bh_finalize");
+  EFM_BH_STAGE(4, st);
   if (dE_all) {
     EFM_DISPATCH_DTYPE(dtype, T, {
-      if (vec) bh_grad_kernel<T, 8><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                                      B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0);
-      else bh_grad_kernel<T, 1><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-                                                                  B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0);
+      if (vec) EFM_LAUNCH((bh_grad_kernel<T, 8>), grid_all, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B_all, (int)D,
+                          row_offset, B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0L);
+      else EFM_LAUNCH((bh_grad_kernel<T, 1>), grid_all, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B_all, (int)D,
+                      row_offset, B_local, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, dE_all, 0L);
     });
     EFM_LAUNCH_CHECK("bh_grad");
+    EFM_BH_STAGE(6, st);
   }
   return EFM_OK;
 }
@@ -837,7 +838,7 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
                                                                 B_local, margin, head_grad, detach, 2, nullptr, nullptr, nullptr,
                                                                 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                 const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), wgt,
-                                                                rheadp, rheadn, rnextp, rnextn, ResPush{});
+                                                                rheadp, rheadn, rnextp, rnextn, DistFin{});
     });
     EFM_LAUNCH_CHECK("bh_finalize(bwd)");
   }
@@ -855,16 +856,41 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
 // Every rank all-gathers (idx_p, idx_n, wgt) of all anchors (12 bytes per anchor) and computes the gradient of ITS rows
 // only: the anchor-role term of its own anchors plus the positive / negative-role terms of every anchor (of any rank)
 // that picked one of its rows.  All embeddings needed are in the gathered batch already.
-// cnt != nullptr: the results of the peers' anchors are still arriving (published by their bh_finalize); every block
-// first waits until the counters of all ranks but `skip` (this rank) have reached `target`.  Loads bypass L1.
+// Multi-GPU form (pull.world > 1): the results of the peers' anchors live in the PEERS' exchange regions.  Every block
+// waits until the local arrival counters of all other ranks have reached `target` (their bh_finalize blocks have all
+// signalled), then every thread fetches its anchor's (idx_p, idx_n, weight) from the owner over NVLink and keeps a local
+// copy for the gradient kernel.
+struct ChainPull {
+  int world, rank;
+  long rows_per_rank;
+  const unsigned long long* cnt;                // [world] local arrival counters
+  unsigned long long target;
+  const int32_t* ip[tc::MAX_PEERS]; const int32_t* in[tc::MAX_PEERS]; const float* w[tc::MAX_PEERS];   // rank r's arrays as mapped here
+};
 __global__ void __launch_bounds__(256)
-bh_chain_kernel(const int32_t* idx_p, const int32_t* idx_n, const float* wgt,
+bh_chain_kernel(int32_t* idx_p, int32_t* idx_n, float* wgt,
                 long n_anchors, long row_begin, long nrows, int32_t* __restrict__ rheadp, int32_t* __restrict__ rheadn,
-                int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn, const unsigned long long* cnt, int world,
-                int skip, unsigned long long target) {
-  if (cnt) {
-    if ((int)threadIdx.x < world && (int)threadIdx.x != skip) tc::wait_counter_thread(cnt + threadIdx.x, target);
+                int32_t* __restrict__ rnextp, int32_t* __restrict__ rnextn, const ChainPull pull) {
+  pdl_trigger();
+  pdl_wait();
+  if (pull.world > 1) {
+    if ((int)threadIdx.x < pull.world && (int)threadIdx.x != pull.rank) tc::wait_counter_thread(pull.cnt + threadIdx.x, pull.target);
     __syncthreads();
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_anchors) {
+      const int owner = (int)(j / pull.rows_per_rank);
+      if (owner != pull.rank) {
+        const int p = __ldcg(pull.ip[owner] + j), n = __ldcg(pull.in[owner] + j);
+        const float w = __ldcg(pull.w[owner] + j);
+        idx_p[j] = p; idx_n[j] = n; wgt[j] = w;
+        if (w != 0.f) {
+          const long pl = p - row_begin, nl = n - row_begin;
+          if (pl >= 0 && pl < nrows) rnextp[j] = atomicExch(&rheadp[pl], (int32_t)j);
+          if (nl >= 0 && nl < nrows) rnextn[j] = atomicExch(&rheadn[nl], (int32_t)j);
+        }
+        return;
+      }
+    }
   }
   const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_anchors || __ldcg(wgt + j) == 0.f) return;
@@ -918,8 +944,9 @@ extern "C" int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype
     });
     EFM_LAUNCH_CHECK("bh_prep(stats)");
   }
-  bh_chain_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(idx_p_all, idx_n_all, wgt_all, B_all, row_offset, B_local, rheadp,
-                                                                rheadn, rnextp, rnextn, nullptr, 0, -1, 0ull);
+  bh_chain_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(const_cast<int32_t*>(idx_p_all), const_cast<int32_t*>(idx_n_all),
+                                                                const_cast<float*>(wgt_all), B_all, row_offset, B_local, rheadp,
+                                                                rheadn, rnextp, rnextn, ChainPull{});
   EFM_LAUNCH_CHECK("bh_chain");
   const unsigned grid = (unsigned)cdiv(B_local, WARPS);
   EFM_DISPATCH_DTYPE(dtype, T, {
@@ -964,9 +991,11 @@ extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long 
 //                 stage) on the peer's arrival counter; the tile schedule is column-block-major starting with the
 //                 local block, and the producer / epilogue warps wait for a peer's stage-A counter right before its
 //                 first tile -> the transfer is hidden behind the tiles of the blocks that are already there
-//   bh_label_table  waits for stage B of all ranks, builds the per-label member table over the global batch
-//   bh_finalize   local anchors; exact mode: publishes (idx_p, idx_n, weight) to every rank (12 B per anchor per rank)
-//   bh_chain      exact mode: waits for the peers' results, chains of all anchors that mined a local row
+//                 afterwards the same warps register their share of the global batch in the per-label member table
+//   bh_finalize   local anchors (waits for stage B); leaves (idx_p, idx_n, weight) of its anchors in the own region and adds
+//                 one arrival per block to every peer's result counter
+//   bh_chain      exact mode: waits for the peers' result counters, FETCHES their anchors' results over NVLink (12 B per
+//                 anchor instead of a dense reduce-scatter of dE) and chains every anchor that mined a local row
 //   bh_grad       local rows only -> dE_local (B_local, D)
 // No NCCL call and no host synchronisation inside the step.
 namespace efm {
@@ -1068,13 +1097,6 @@ extern "C" int efm_ipc_release(void* mapped) {
   return EFM_OK;
 }
 
-static thread_local cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
-extern "C" int efm_bh_profile_events(void* ev_start, void* ev_end) {
-  g_prof_ev[0] = static_cast<cudaEvent_t>(ev_start);
-  g_prof_ev[1] = static_cast<cudaEvent_t>(ev_end);
-  return EFM_OK;
-}
-
 extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_local, long B_local, long D, int dtype,
                                    float margin, const float* head_grad, int flags, int world, int rank,
                                    void* const* regions, unsigned long long step, float* loss, int32_t* idx_p,
@@ -1120,6 +1142,7 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
   const size_t es = dtype_size(dtype);
   const unsigned grid_loc = (unsigned)(B / WARPS);
 
+  EFM_BH_STAGE(0, st);
   EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));
   // 1. local rows -> block `rank` of this step's buffer
   EFM_DISPATCH_DTYPE(dtype, T, {
@@ -1128,6 +1151,7 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   });
   EFM_LAUNCH_CHECK("bh_prep(local)");
+  EFM_BH_STAGE(1, st);
   // 2. Gram + mining + exchange
   unsigned long long target_ab = 0;
   {
@@ -1148,53 +1172,55 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
     cp.seg[3] = {reinterpret_cast<const uint8_t*>(nrm + row0), boff + X.nrm + (size_t)row0 * 4, (unsigned long long)B * 4};
     cp.seg[4] = {static_cast<const uint8_t*>(E_local), boff + X.E + (size_t)row0 * D * es, (unsigned long long)B * D * es};
     cp.cnt_a_off = X.cnt_a; cp.cnt_b_off = X.cnt_b;
+    cp.tab_lab = lab; cp.tab_rows = B_all;                               // label table of the global batch, built by the same warps
+    cp.hkeys = hkeys; cp.hcnt = hcnt; cp.hmem = hmem; cp.hhead = hhead; cp.hnext = hnext; cp.hslot = hslot; cp.tbits = L.tbits;
     MineEpi::Params ep{sq, lab, kneg, (int)row0};
-    if (g_prof_ev[0]) EFM_CUDA(cudaEventRecord(g_prof_ev[0], st));
-    const int rc = tc::launch_gram_mh<MineEpi, 1, 2, true>(xm + row0 * X.Dp, xm, g, ep, grid, st, &cp);
+    const int rc = tc::launch_gram_mh<MineEpi, 1, 2, true>(xm + row0 * X.Dp, xm, g, ep, grid, st, &cp, true);
     if (rc) return rc;
-    if (g_prof_ev[1]) EFM_CUDA(cudaEventRecord(g_prof_ev[1], st));
   }
-  // 3. label table over the global batch (waits for stage B: the original rows of every rank, own copy included)
-  bh_label_table_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(lab, B_all, hkeys, hcnt, hmem, hhead, hnext, hslot, L.tbits,
-                                                                     reinterpret_cast<const unsigned long long*>(own + X.cnt_b), world,
-                                                                     target_ab);
-  EFM_LAUNCH_CHECK("bh_label_table");
-  // 4. finalize the local anchors
-  ResPush rp{};
-  {                                                                      // published in every mode, so the result counters of all
-    rp.world = world; rp.rank = rank;                                    // ranks advance in lockstep whatever mix of flags is used
-    for (int r = 0; r < world; ++r) {
-      uint8_t* b = static_cast<uint8_t*>(regions[r]) + boff;
-      rp.ip[r] = reinterpret_cast<int32_t*>(b + X.rip); rp.in[r] = reinterpret_cast<int32_t*>(b + X.rin);
-      rp.w[r] = reinterpret_cast<float*>(b + X.rw);
-      rp.cnt[r] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(regions[r]) + X.cnt_c) + rank;
-    }
-  }
+  EFM_BH_STAGE(2, st);
+  // 3. finalize the local anchors (waits for stage B: the original rows of every rank, own copy included)
+  DistFin df{};
+  df.world = world; df.rank = rank;
+  df.wait_b = reinterpret_cast<const unsigned long long*>(own + X.cnt_b); df.target_b = target_ab;
+  df.rip = rip; df.rin = rin; df.rw = rw;                                // published in every mode, so the result counters of all
+  for (int r = 0; r < world; ++r)                                        // ranks advance in lockstep whatever mix of flags is used
+    df.sig[r] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(regions[r]) + X.cnt_c) + rank;
   const bool chains_local = dE_local && !exact;
   EFM_DISPATCH_DTYPE(dtype, T, {
-    bh_finalize_kernel<T, true><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row0, B, margin, head_grad,
-                                                                 chains_local ? 1 : 0, 1, kpos, kneg, xm, X.Dp, lab, hcnt, hmem, hhead,
-                                                                 hnext, hslot, loss, idx_p, idx_n, chains_local ? wgt : nullptr,
-                                                                 chains_local ? rheadp : nullptr, rheadn, rnextp, rnextn, rp);
+    EFM_LAUNCH((bh_finalize_kernel<T, true>), grid_loc, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B_all, (int)D, row0, B,
+               margin, head_grad, chains_local ? 1 : 0, 1, kpos, kneg, xm, X.Dp, lab, hcnt, hmem, hhead, hnext, hslot, loss, idx_p,
+               idx_n, chains_local ? wgt : nullptr, chains_local ? rheadp : nullptr, rheadn, rnextp, rnextn, df);
   });
   EFM_LAUNCH_CHECK("bh_finalize(dist)");
+  EFM_BH_STAGE(4, st);
   if (!dE_local) return EFM_OK;
   // 5./6. gradient of the local rows
   if (exact) {
-    bh_chain_kernel<<<(unsigned)cdiv(B_all, 256), 256, 0, st>>>(rip, rin, rw, B_all, row0, B, rheadp, rheadn, rnextp, rnextn,
-                                                                  reinterpret_cast<const unsigned long long*>(own + X.cnt_c), world, rank,
-                                                                  step * (unsigned long long)grid_loc);
+    ChainPull pull{};
+    pull.world = world; pull.rank = rank; pull.rows_per_rank = B;
+    pull.cnt = reinterpret_cast<const unsigned long long*>(own + X.cnt_c);
+    pull.target = step * (unsigned long long)grid_loc;                   // one arrival per finalize block of the owner per step
+    for (int r = 0; r < world; ++r) {
+      const uint8_t* b = static_cast<const uint8_t*>(regions[r]) + boff;
+      pull.ip[r] = reinterpret_cast<const int32_t*>(b + X.rip); pull.in[r] = reinterpret_cast<const int32_t*>(b + X.rin);
+      pull.w[r] = reinterpret_cast<const float*>(b + X.rw);
+    }
+    EFM_LAUNCH(bh_chain_kernel, (unsigned)cdiv(B_all, 256), 256, 0, st, true, rip, rin, rw, B_all, row0, B, rheadp, rheadn, rnextp, rnextn,
+               pull);
     EFM_LAUNCH_CHECK("bh_chain(dist)");
+    EFM_BH_STAGE(5, st);
     EFM_DISPATCH_DTYPE(dtype, T, {
-      bh_grad_kernel<T, 8><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B, (int)D, 0, B_all, rip, rin, rw, rheadp,
-                                                            rheadn, rnextp, rnextn, dE_local, row0);
+      EFM_LAUNCH((bh_grad_kernel<T, 8>), grid_loc, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B, (int)D, 0L, B_all, rip, rin,
+                 rw, rheadp, rheadn, rnextp, rnextn, dE_local, row0);
     });
   } else {
     EFM_DISPATCH_DTYPE(dtype, T, {
-      bh_grad_kernel<T, 8><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B, (int)D, row0, B, idx_p, idx_n, wgt,
-                                                            rheadp + row0, rheadn + row0, rnextp, rnextn, dE_local, row0);
+      EFM_LAUNCH((bh_grad_kernel<T, 8>), grid_loc, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B, (int)D, row0, B, idx_p,
+                 idx_n, wgt, rheadp + row0, rheadn + row0, rnextp, rnextn, dE_local, row0);
     });
   }
   EFM_LAUNCH_CHECK("bh_grad(dist)");
+  EFM_BH_STAGE(6, st);
   return EFM_OK;
 }

@@ -49,6 +49,40 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// The kernels of one batch-hard step are launched with programmatic stream serialization: a kernel's CTAs may be
+// scheduled while the previous kernel of the stream is still draining (it calls pdl_trigger() at its top), and block in
+// pdl_wait() until that kernel has completed and its memory is visible.  Both are no-ops for plain launches.
+// EFM_PDL=0 switches the launch attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute at[2];
+  LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, int cluster = 1) {
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    unsigned n = 0;
+    if (cluster > 1) {
+      at[n].id = cudaLaunchAttributeClusterDimension;
+      at[n].val.clusterDim.x = (unsigned)cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (pdl && pdl_enabled()) {
+      at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
+  }
+};
+// kernel names with template commas go in parentheses: EFM_LAUNCH((k<T, V>), grid, block, smem, st, pdl, args...)
+#define EFM_LAUNCH(kernel, grid, block, smem, st, pdl, ...)                  \
+  do {                                                                       \
+    ::efm::LaunchCfg _lc(dim3(grid), dim3(block), (smem), (st), (pdl));      \
+    EFM_CUDA(cudaLaunchKernelEx(&_lc.cfg, kernel, __VA_ARGS__));             \
+  } while (0)
+
 // ---- storage-type traits ------------------------------------------------------------------------
 template <typename T> struct El;
 template <> struct El<float> {

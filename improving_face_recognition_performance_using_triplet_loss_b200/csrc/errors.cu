@@ -1,5 +1,6 @@
 // errors.cu -- thread-local error message + misc ABI entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -12,6 +13,12 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EFM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

@@ -80,7 +80,33 @@ struct CommParams {
   uint8_t* peer[MAX_PEERS];              // base of rank r's exchange region as mapped in this process (peer[rank] = own)
   PushSeg seg[MAX_PUSH_SEGS];
   unsigned long long cnt_a_off, cnt_b_off;   // offsets of the u64[world] arrival counters inside a region
+  // Second job of the exchange warp, after its pushes: once stage A of every rank has arrived (the labels of the whole
+  // global batch are local), register this CTA's share of the rows in the per-label member table that the finalize
+  // kernel reads -- the table build is hidden behind the Gram tiles instead of being a kernel of its own.
+  const int32_t* tab_lab;                // (tab_rows) labels, nullptr = no table job
+  long tab_rows;
+  unsigned long long* hkeys; int32_t* hcnt; int32_t* hmem; int32_t* hhead; int32_t* hnext; int32_t* hslot; int tbits;
 };
+
+// register `row` with its label: open-addressing table of 64-bit tags; the first 8 members of a label are stored inline
+// (no pointer chasing in the finalize kernel), further members go to an overflow chain.  Tables start as all-ones bytes.
+__device__ __forceinline__ void label_table_insert(int32_t lab, long row, unsigned long long* __restrict__ hkeys,
+                                                   int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem,
+                                                   int32_t* __restrict__ hhead, int32_t* __restrict__ hnext,
+                                                   int32_t* __restrict__ hslot, int tbits) {
+  const unsigned long long tag = (unsigned long long)(uint32_t)lab;     // upper half 0: never equals EMPTY (~0)
+  const uint32_t mask = (1u << tbits) - 1u;
+  uint32_t sl = ((uint32_t)lab * 2654435761u) >> (32 - tbits);
+  for (;;) {
+    const unsigned long long old = atomicCAS(&hkeys[sl], ~0ull, tag);
+    if (old == ~0ull || old == tag) break;
+    sl = (sl + 1) & mask;
+  }
+  hslot[row] = (int32_t)sl;
+  const int pos = atomicAdd(&hcnt[sl], 1) + 1;                       // counter starts at -1
+  if (pos < 8) hmem[sl * 8 + pos] = (int32_t)row;
+  else hnext[row] = atomicExch(&hhead[sl], (int32_t)row);
+}
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -463,6 +489,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers + TMEM of both CTAs are live past this point
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();                                                     // the next kernel's CTAs may take this SM as soon as we exit
+  pdl_wait();                                                        // everything above overlapped the previous kernel's tail
   if (threadIdx.x == 0) EFM_TRACE(1);
 
   if (warp == PRODUCER_WARP) {
@@ -618,6 +646,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (i > 0) Epi::row_end(ep, g, row, part, st);
   } else if (COMM && warp == MMA_WARP + 1) {
     if (cp.world > 1 || cp.self_b) comm_push(cp, (int)blockIdx.x, (int)gridDim.x);
+    if (cp.tab_lab) {
+      if (g.ready)
+        for (int r = 0; r < cp.world; ++r)
+          if (r != cp.rank) wait_counter(g.ready + r, g.ready_target);       // labels of every rank are here
+      const long lo = cp.tab_rows * blockIdx.x / gridDim.x, hi = cp.tab_rows * (blockIdx.x + 1) / gridDim.x;
+      for (long row = lo + lane; row < hi; row += 32)
+        label_table_insert(__ldcg(cp.tab_lab + row), row, cp.hkeys, cp.hcnt, cp.hmem, cp.hhead, cp.hnext, cp.hslot, cp.tbits);
+    }
   }
 
   tc_fence_before();
@@ -636,7 +672,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, long rows, long Kp, int b
 
 template <class Epi, int MH, int CG, bool COMM = false>
 int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Epi::Params& ep, int grid, cudaStream_t st,
-                   const CommParams* cp = nullptr) {
+                   const CommParams* cp = nullptr, bool pdl = false) {
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, 128);       // A box: 128 rows per TMA (MH = 2 issues it per 256-row block)
   if (MH == 2) rc = make_tmap_bf16(&tmA, A, g.M, (long)g.nk * BK, Shape<MH>::BM);
@@ -654,17 +690,8 @@ int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Ep
   CommParams none{};
   const CommParams& c = cp ? *cp : none;
   constexpr unsigned NT = THREADS + (COMM ? 32 : 0);
-  if (CG == 2) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    EFM_CUDA(cudaLaunchKernelEx(&cfg, gram_kernel<Epi, MH, CG, COMM>, tmA, tmB, g, ep, c));
-  } else {
-    gram_kernel<Epi, MH, CG, COMM><<<grid, NT, smem, st>>>(tmA, tmB, g, ep, c);
-  }
+  LaunchCfg lc(dim3((unsigned)grid), dim3(NT), smem, st, pdl, CG);
+  EFM_CUDA(cudaLaunchKernelEx(&lc.cfg, gram_kernel<Epi, MH, CG, COMM>, tmA, tmB, g, ep, c));
   EFM_LAUNCH_CHECK("gram_kernel");
   return EFM_OK;
 }
@@ -721,11 +748,11 @@ inline int plan_gram(GramParams& g, int mh, int sched_mode, int smem_extra = 0, 
 
 template <class Epi>
 int launch_gram(const void* A, const void* B, int mh, const GramParams& g, const typename Epi::Params& ep, int grid,
-                cudaStream_t st, int cg = 1) {
+                cudaStream_t st, int cg = 1, bool pdl = false) {
   EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "gram: K = %d leaves no shared memory for the B pipeline", g.nk * BK);
-  if (cg == 2) return launch_gram_mh<Epi, 1, 2>(A, B, g, ep, grid, st);
-  if (mh == 2) return launch_gram_mh<Epi, 2, 1>(A, B, g, ep, grid, st);
-  return launch_gram_mh<Epi, 1, 1>(A, B, g, ep, grid, st);
+  if (cg == 2) return launch_gram_mh<Epi, 1, 2>(A, B, g, ep, grid, st, nullptr, pdl);
+  if (mh == 2) return launch_gram_mh<Epi, 2, 1>(A, B, g, ep, grid, st, nullptr, pdl);
+  return launch_gram_mh<Epi, 1, 1>(A, B, g, ep, grid, st, nullptr, pdl);
 }
 
 }  // namespace tc

@@ -153,8 +153,9 @@ int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype, int flags
  * buffers and the value the arrival counters are compared with; nothing is reset between steps).
  *
  * The step enqueues prep (local rows) -> Gram + mining kernel that also PUSHES this rank's rows into every peer's
- * region over NVLink and waits, column block by column block, for the peers' rows (see csrc/bh.cu) -> label table ->
- * finalize (exact mode publishes 12 bytes per anchor to every rank) -> gradient of the local rows.  No NCCL call, no
+ * region over NVLink, waits, column block by column block, for the peers' rows and builds the label table of the
+ * global batch (see csrc/bh.cu) -> finalize -> (exact mode) chain kernel that fetches 12 bytes per anchor from the
+ * owners over NVLink -> gradient of the local rows.  No NCCL call, no
  * host synchronisation.  Results equal efm_bh_triplet_fwd_bwd on the concatenated batch: loss / idx_p / idx_n
  * (B_local; indices are global rows), dE_local (B_local, D) fp32 or NULL (forward only).  EFM_BH_DETACH_GATHERED:
  * gradient only through roles played by local rows of local anchors (no result exchange).  Mining always runs on the
@@ -171,9 +172,12 @@ int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_local, long B
                         float margin, const float* head_grad, int flags, int world, int rank,
                         void* const* regions, unsigned long long step, float* loss, int32_t* idx_p,
                         int32_t* idx_n, float* dE_local, void* workspace, size_t ws_bytes, void* stream);
-/* Profiling aid: the next efm_bh_dist_fwd_bwd calls of this thread record these cudaEvent_t (passed as void*) right
- * before / after the Gram + mining + exchange kernel on the call's stream; (NULL, NULL) switches it off. */
-int efm_bh_profile_events(void* ev_start, void* ev_end);
+/* Profiling aid: the following efm_bh_triplet_fwd_bwd / efm_bh_dist_fwd_bwd calls of this thread record
+ * events[i] (cudaEvent_t passed as void*, NULL entries skipped) on the call's stream at stage boundary i:
+ * 0 step start, 1 after memset + prep, 2 after the Gram + mining (+ exchange) kernel, 3 unused, 4 after finalize, 5 after the chain kernel (multi-GPU exact gradient only), 6 after
+ * the gradient kernel.  n = 0 switches it off. */
+#define EFM_BH_PROFILE_EVENTS 7
+int efm_bh_profile_events(void* const* events, int n);
 
 /* ---- a8-a11: gallery scoring ---------------------------------------------------------------------
  * simd_dot (Feature.hpp:273-293) + Compare_Face_From_DB (:345-392 argmax, :295-343 top-K) +
