@@ -225,7 +225,7 @@ def run_ours(args):
     fused = world > 1 and name == "c3"
     if fused:
         try:
-            px = D.PeerExchange(B, DIM, torch.bfloat16, device=dev)
+            px = D.PeerExchange(B, DIM, torch.bfloat16, device=dev, multicast={"auto": None, "on": True, "off": False}[args.multicast])
         except Exception as e:  # noqa: BLE001  (no peer access / IPC on this box: say so and use the NCCL form)
             if rank == 0:
                 print("bench: fused exchange unavailable (%s); using the NCCL all-gather form" % e, file=sys.stderr, flush=True)
@@ -235,6 +235,7 @@ def run_ours(args):
         if not int(ok) and px is not None:
             px.close(); px = None
         fused = bool(int(ok))
+    xmode = px.mode if px is not None else ""
     if fused:
         dE_loc = torch.empty((B, DIM), dtype=torch.float32, device=dev)
         launches_per_step = ["bh_prep", "gram_kernel<MineEpi,COMM>", "bh_finalize", "bh_chain", "bh_grad"]
@@ -242,7 +243,7 @@ def run_ours(args):
         def step():
             px.steps += 1
             L.check(L.lib.efm_bh_dist_fwd_bwd(L.ptr(E_loc), L.ptr(y_loc), B, DIM, dt, MARGIN, None, flags, world, rank, px.regions,
-                                              px.steps, L.ptr(loss), L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE_loc), L.ptr(px.ws),
+                                              px.mc, px.steps, L.ptr(loss), L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE_loc), L.ptr(px.ws),
                                               px.ws.numel(), L.stream()))
     else:
         ws = L.workspace(L.lib.efm_bh_workspace_bytes(B, G, DIM, dt, flags), dev)
@@ -414,7 +415,8 @@ def run_ours(args):
         achieved = flops / (t_kernel * 1e-3) / 1e12
         peak = float(pk["bf16_tflops"])                                # burst figure: kernel timed alone
         if fused:
-            par = "dp%d, exchange fused into the Gram kernel over NVLink peer memory (no NCCL); exact gradient via 12 B/anchor" % world
+            par = "dp%d, exchange fused into the Gram kernel over NVLink peer memory (%s; no NCCL); exact gradient via 12 B/anchor" % (
+                world, xmode)
             kname = "gram_kernel<MineEpi,COMM> (tcgen05 Gram + mining epilogue + NVLink push/arrival waits), timed inside the step"
         elif world > 1:
             par = "dp%d NCCL all-gather fwd / reduce-scatter bwd" % world
@@ -468,6 +470,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c3-strong", "c3-nccl", "c3-weak"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"], help="N > 1: NVLS multicast pushes (auto = if available)")
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same C3 job")
     args = ap.parse_args()
     if args.impl == "reference":

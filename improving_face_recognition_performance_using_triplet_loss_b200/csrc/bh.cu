@@ -1099,11 +1099,12 @@ extern "C" int efm_ipc_release(void* mapped) {
 
 extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_local, long B_local, long D, int dtype,
                                    float margin, const float* head_grad, int flags, int world, int rank,
-                                   void* const* regions, unsigned long long step, float* loss, int32_t* idx_p,
+                                   void* const* regions, void* mc_region, unsigned long long step, float* loss, int32_t* idx_p,
                                    int32_t* idx_n, float* dE_local, void* workspace, size_t ws_bytes, void* stream) {
   { const int rc = dist_check_shape("efm_bh_dist_fwd_bwd", B_local, world, rank, D, dtype); if (rc) return rc; }
   EFM_REQUIRE(E_local && labels_local && regions && loss && idx_p && idx_n && workspace, EFM_E_ARG, "efm_bh_dist_fwd_bwd: null pointer");
   EFM_REQUIRE(step >= 1, EFM_E_ARG, "efm_bh_dist_fwd_bwd: step counts from 1 (the same value on every rank)");
+  EFM_REQUIRE(!mc_region || aligned(mc_region, 256), EFM_E_ALIGN, "efm_bh_dist_fwd_bwd: multicast region must be 256-byte aligned");
   EFM_REQUIRE(aligned(workspace, 256) && aligned(E_local, 16) && (!dE_local || aligned(dE_local, 16)), EFM_E_ALIGN,
               "efm_bh_dist_fwd_bwd: workspace must be 256-byte, E_local / dE_local 16-byte aligned");
   for (int r = 0; r < world; ++r) EFM_REQUIRE(regions[r] && aligned(regions[r], 256), EFM_E_ARG, "efm_bh_dist_fwd_bwd: region %d missing", r);
@@ -1160,12 +1161,15 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
     g.phases = world; g.phase0 = rank;
     const int grid = tc::plan_gram(g, 1, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, 2);
     EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "efm_bh_dist_fwd_bwd: D = %ld leaves no shared memory for the B pipeline", D);
-    target_ab = step * (unsigned long long)grid;                         // every CTA of a sender adds 1 per (peer, stage) per step
+    // arrivals per (sender, stage, step): unicast -- one per CTA (the exchange warp that serves the destination);
+    // multicast -- one per exchange warp (they share every segment)
+    target_ab = step * (unsigned long long)grid * ((mc_region && world > 1) ? tc::COMM_WARPS : 1);
     g.ready = reinterpret_cast<const unsigned long long*>(own + X.cnt_a);
     g.ready_target = target_ab;
     tc::CommParams cp{};
     cp.world = world; cp.rank = rank; cp.nseg_a = 4; cp.nseg = 5; cp.self_b = 1;
     for (int r = 0; r < world; ++r) cp.peer[r] = static_cast<uint8_t*>(regions[r]);
+    cp.mc = world > 1 ? static_cast<uint8_t*>(mc_region) : nullptr;
     cp.seg[0] = {reinterpret_cast<const uint8_t*>(xm + row0 * X.Dp), boff + X.xm + (size_t)row0 * X.Dp * 2, (unsigned long long)B * X.Dp * 2};
     cp.seg[1] = {reinterpret_cast<const uint8_t*>(sq + row0), boff + X.sq + (size_t)row0 * 4, (unsigned long long)B * 4};
     cp.seg[2] = {reinterpret_cast<const uint8_t*>(lab + row0), boff + X.lab + (size_t)row0 * 4, (unsigned long long)B * 4};

@@ -46,7 +46,8 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;        // 227 KB opt-in maximum per CTA
 
 struct GramParams {
-  unsigned long long* trace;   // profiling aid (env EFM_GRAM_TRACE=<device ptr>): 8 globaltimer stamps per CTA
+  unsigned long long* trace;   // profiling aid (env EFM_GRAM_TRACE=<device ptr>): 16 u64 per CTA -- globaltimer stamps 0-7 of the
+                               // tile pipeline, 8-12 of the exchange warp, 13/14 = ns / count of the producer's peer waits
   int debug;             // profiling aid (env EFM_GRAM_DEBUG): 1 = skip the epilogue work, 2 = TMEM loads only
   int M, N;              // valid rows of A / rows of B (= Gram columns)
   int nk;                // K blocks of 64 (Kp = 64 * nk)
@@ -71,6 +72,9 @@ struct GramParams {
 // of one CTA for one destination: fence.sys, then one release-add on the destination's arrival counter for this rank.
 constexpr int MAX_PEERS = 8;
 constexpr int MAX_PUSH_SEGS = 6;
+constexpr int COMM_WARPS = 2;            // exchange warps per CTA (COMM kernels); they alternate over the destinations, so one
+                                         // keeps the link busy while the other sits in the system-scope fence before its signal
+constexpr int PUSH_DEPTH = 8;            // 16-byte loads in flight per lane
 struct PushSeg { const uint8_t* src; unsigned long long dst_off; unsigned long long bytes; };   // 16-byte multiples
 struct CommParams {
   int world, rank;
@@ -78,6 +82,9 @@ struct CommParams {
   int self_b;                            // stage B is also copied into this rank's OWN region (last), so that the
                                          // gathered rows are contiguous locally without a separate copy
   uint8_t* peer[MAX_PEERS];              // base of rank r's exchange region as mapped in this process (peer[rank] = own)
+  uint8_t* mc;                           // NVLS multicast alias of ALL regions (nullptr: unicast pushes, one per peer).  One
+                                         // multimem.st is replicated by the NVSwitch into every rank's region (own included), so
+                                         // a rank sends its rows ONCE instead of world - 1 times
   PushSeg seg[MAX_PUSH_SEGS];
   unsigned long long cnt_a_off, cnt_b_off;   // offsets of the u64[world] arrival counters inside a region
   // Second job of the exchange warp, after its pushes: once stage A of every rank has arrived (the labels of the whole
@@ -194,7 +201,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define EFM_TRACE(slot) do { if (g.trace && (threadIdx.x & 31) == 0) g.trace[(size_t)blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
+constexpr int TRACE_SLOTS = 16;
+#define EFM_TRACE(slot) do { if (g.trace && (threadIdx.x & 31) == 0) g.trace[(size_t)blockIdx.x * TRACE_SLOTS + (slot)] = gtimer(); } while (0)
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile(
@@ -233,37 +241,87 @@ __device__ __forceinline__ void wait_counter(const unsigned long long* p, unsign
   if ((threadIdx.x & 31) == 0) wait_counter_thread(p, target);
   __syncwarp();
 }
-// one warp copies its CTA's share of a segment: 16-byte units, 8 loads in flight per lane, plain (posted) stores
+// one warp copies its share of a segment: 16-byte units, PUSH_DEPTH loads in flight per lane, plain (posted) stores
 __device__ __forceinline__ void push_share(uint8_t* dst, const uint8_t* src, unsigned long long bytes, int part, int nparts, int lane) {
   const long U = (long)(bytes >> 4);
   const long lo = U * part / nparts, hi = U * (part + 1) / nparts;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
   long u = lo + lane;
-  for (; u + 7 * 32 < hi; u += 8 * 32) {
-    uint4 v[8];
+  for (; u + (PUSH_DEPTH - 1) * 32 < hi; u += PUSH_DEPTH * 32) {
+    uint4 v[PUSH_DEPTH];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = s4[u + k * 32];
+    for (int k = 0; k < PUSH_DEPTH; ++k) v[k] = __ldcg(s4 + u + k * 32);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) d4[u + k * 32] = v[k];
+    for (int k = 0; k < PUSH_DEPTH; ++k) d4[u + k * 32] = v[k];
   }
-  for (; u < hi; u += 32) d4[u] = s4[u];
+  for (; u < hi; u += 32) d4[u] = __ldcg(s4 + u);
 }
-// the push of one CTA (`part` of `nparts`), executed by one warp
-__device__ __forceinline__ void comm_push(const CommParams& cp, int part, int nparts) {
+// ---- NVLS multicast (multimem) ------------------------------------------------------------------------------
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+__device__ __forceinline__ void multimem_red_release_add_u64(void* mc_addr, unsigned long long v) {
+  asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(mc_addr), "l"(v) : "memory");
+}
+// writes through the multicast alias are read through the unicast address: order the two aliases (reader side)
+__device__ __forceinline__ void fence_proxy_alias() { asm volatile("fence.proxy.alias;" ::: "memory"); }
+
+__device__ __forceinline__ void push_share_mc(uint8_t* mc_dst, const uint8_t* src, unsigned long long bytes, int part, int nparts, int lane) {
+  const long U = (long)(bytes >> 4);
+  const long lo = U * part / nparts, hi = U * (part + 1) / nparts;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(mc_dst);
+  long u = lo + lane;
+  for (; u + (PUSH_DEPTH - 1) * 32 < hi; u += PUSH_DEPTH * 32) {
+    uint4 v[PUSH_DEPTH];
+#pragma unroll
+    for (int k = 0; k < PUSH_DEPTH; ++k) v[k] = __ldcg(s4 + u + k * 32);
+#pragma unroll
+    for (int k = 0; k < PUSH_DEPTH; ++k) multimem_st_v4(d4 + u + k * 32, v[k]);
+  }
+  for (; u < hi; u += 32) multimem_st_v4(d4 + u, __ldcg(s4 + u));
+}
+// Multicast push of exchange warp `part` of `nparts` (all exchange warps of the grid share every segment): one pass per
+// stage, one fence, one multicast release-add that bumps this rank's arrival counter in EVERY region.
+__device__ __forceinline__ void comm_push_mc(const CommParams& cp, int part, int nparts, unsigned long long* trace) {
   const int lane = threadIdx.x & 31;
   for (int stage = 0; stage < 2; ++stage) {
+    if (stage && trace && lane == 0) trace[9] = gtimer();
+    const int s0 = stage ? cp.nseg_a : 0, s1 = stage ? cp.nseg : cp.nseg_a;
+    if (s0 == s1) continue;
+    for (int s = s0; s < s1; ++s) push_share_mc(cp.mc + cp.seg[s].dst_off, cp.seg[s].src, cp.seg[s].bytes, part, nparts, lane);
+    const unsigned long long tf = trace ? gtimer() : 0ull;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      multimem_red_release_add_u64(cp.mc + (stage ? cp.cnt_b_off : cp.cnt_a_off) + 8ull * cp.rank, 1ull);
+      if (trace) trace[15] += gtimer() - tf;
+    }
+  }
+}
+
+// The push of one CTA (`part` of `nparts`): exchange warp `cw` serves every COMM_WARPS-th destination.
+__device__ __forceinline__ void comm_push(const CommParams& cp, int part, int nparts, int cw, unsigned long long* trace) {
+  const int lane = threadIdx.x & 31;
+  for (int stage = 0; stage < 2; ++stage) {
+    if (stage && trace && lane == 0) trace[9] = gtimer();            // this warp's stage A pushed
     const int s0 = stage ? cp.nseg_a : 0, s1 = stage ? cp.nseg : cp.nseg_a;
     if (s0 == s1) continue;
     const int last = (stage && cp.self_b) ? cp.world : cp.world - 1; // ph = world: this rank's own region
     for (int ph = 1; ph <= last; ++ph) {
+      if ((ph % COMM_WARPS) != cw) continue;
       int dest = cp.rank - ph; if (dest < 0) dest += cp.world;       // the receiver that reaches this rank's block at phase ph
       uint8_t* base = cp.peer[dest];
       for (int s = s0; s < s1; ++s) push_share(base + cp.seg[s].dst_off, cp.seg[s].src, cp.seg[s].bytes, part, nparts, lane);
+      const unsigned long long tf = trace ? gtimer() : 0ull;
       __threadfence_system();
       __syncwarp();
-      if (lane == 0)
+      if (lane == 0) {
         red_release_sys_add_u64(reinterpret_cast<unsigned long long*>(base + (stage ? cp.cnt_b_off : cp.cnt_a_off)) + cp.rank, 1ull);
+        if (trace) trace[15] += gtimer() - tf;                       // time spent in fences
+      }
     }
   }
 }
@@ -439,9 +497,9 @@ template <int MH> inline int pick_stages(int nk, int extra) {
 // which reads both halves, so every SM pulls half the B bytes from L2 and reads half the B bytes from shared memory per
 // MAC.  Barriers: full / a_full / acc_empty live in the leader (TMA of both CTAs credits the leader, the peer's epilogue
 // arrives remotely); empty / a_empty / acc_full are signalled in both CTAs by multicast tcgen05.commit.
-// COMM: a 19th warp pushes this rank's rows to the peers' exchange regions while the tiles run (see CommParams).
+// COMM: COMM_WARPS extra warps push this rank's rows to the peers' exchange regions while the tiles run (see CommParams).
 template <class Epi, int MH, int CG, bool COMM>
-__global__ void __launch_bounds__(THREADS + (COMM ? 32 : 0), 1)
+__global__ void __launch_bounds__(THREADS + (COMM ? 32 * COMM_WARPS : 0), 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams g,
             const typename Epi::Params ep, const CommParams cp) {
   static_assert(CG == 1 || MH == 1, "the 2-CTA path uses the 128 x 256 per-CTA shape");
@@ -502,8 +560,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     while (it.next()) {
       const int rb = it.rb, ct = it.ct();
       if (it.new_phase && it.ph > 0 && g.ready) {                    // a peer's column block: wait until it has landed
+        const unsigned long long tw = g.trace ? gtimer() : 0ull;
         wait_counter(g.ready + it.block(), g.ready_target);
+        fence_proxy_alias();                                         // the rows may have been written through the multicast alias
         fence_proxy_async_all();                                     // remote generic-proxy writes -> our TMA (async proxy) reads
+        if (g.trace && lane == 0) {
+          g.trace[(size_t)blockIdx.x * TRACE_SLOTS + 13] += gtimer() - tw;
+          g.trace[(size_t)blockIdx.x * TRACE_SLOTS + 14] += 1;
+        }
       }
       if (it.new_rb) {                                               // new row block: (re)load the resident A block
         if (!first) { mbar_wait(bar_a_empty, a_empty_phase); a_empty_phase ^= 1; }
@@ -600,7 +664,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     TileIter<CG> nx(g);
     bool has = nx.next();
     if (has) {
-      if (nx.ph > 0 && g.ready) wait_counter(g.ready + nx.block(), g.ready_target);   // no tile in the local block
+      if (nx.ph > 0 && g.ready) { wait_counter(g.ready + nx.block(), g.ready_target); fence_proxy_alias(); }   // no tile in the local block
       Epi::prefetch(ep, g, scratch, 0, nx.ct() * BN + cs * COLS_PER_WARP);
     }
     int i = 0;
@@ -614,7 +678,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       has = nx.next();                                               // nx now describes the tile after this one
       Epi::prefetch_wait();                                          // this tile's per-column data has landed
       if (has) {                                                     // next tile's data: in flight during this tile
-        if (nx.new_phase && g.ready) wait_counter(g.ready + nx.block(), g.ready_target);   // ... once its block has arrived
+        if (nx.new_phase && g.ready) { wait_counter(g.ready + nx.block(), g.ready_target); fence_proxy_alias(); }   // ... once its block has arrived
         Epi::prefetch(ep, g, scratch, (i + 1) & 1, nx.ct() * BN + cs * COLS_PER_WARP);
       }
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
@@ -644,15 +708,25 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ++i;
     }
     if (i > 0) Epi::row_end(ep, g, row, part, st);
-  } else if (COMM && warp == MMA_WARP + 1) {
-    if (cp.world > 1 || cp.self_b) comm_push(cp, (int)blockIdx.x, (int)gridDim.x);
+  } else if (COMM && warp > MMA_WARP) {
+    const int cw = warp - (MMA_WARP + 1);
+    const int part = (int)blockIdx.x * COMM_WARPS + cw, nparts = (int)gridDim.x * COMM_WARPS;
+    const bool tr = g.trace && cw == 1;                              // warp 1 serves the first destination
+    if (tr) EFM_TRACE(8);
+    if (cp.mc) comm_push_mc(cp, part, nparts, tr ? g.trace + (size_t)blockIdx.x * TRACE_SLOTS : nullptr);
+    else if (cp.world > 1 || cp.self_b)
+      comm_push(cp, (int)blockIdx.x, (int)gridDim.x, cw, tr ? g.trace + (size_t)blockIdx.x * TRACE_SLOTS : nullptr);
+    if (tr) EFM_TRACE(10);
     if (cp.tab_lab) {
       if (g.ready)
         for (int r = 0; r < cp.world; ++r)
           if (r != cp.rank) wait_counter(g.ready + r, g.ready_target);       // labels of every rank are here
-      const long lo = cp.tab_rows * blockIdx.x / gridDim.x, hi = cp.tab_rows * (blockIdx.x + 1) / gridDim.x;
+      fence_proxy_alias();
+      if (tr) EFM_TRACE(11);
+      const long lo = cp.tab_rows * part / nparts, hi = cp.tab_rows * (part + 1) / nparts;
       for (long row = lo + lane; row < hi; row += 32)
         label_table_insert(__ldcg(cp.tab_lab + row), row, cp.hkeys, cp.hcnt, cp.hmem, cp.hhead, cp.hnext, cp.hslot, cp.tbits);
+      if (tr) EFM_TRACE(12);
     }
   }
 
@@ -689,7 +763,7 @@ int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Ep
   }
   CommParams none{};
   const CommParams& c = cp ? *cp : none;
-  constexpr unsigned NT = THREADS + (COMM ? 32 : 0);
+  constexpr unsigned NT = THREADS + (COMM ? 32 * COMM_WARPS : 0);
   LaunchCfg lc(dim3((unsigned)grid), dim3(NT), smem, st, pdl, CG);
   EFM_CUDA(cudaLaunchKernelEx(&lc.cfg, gram_kernel<Epi, MH, CG, COMM>, tmA, tmB, g, ep, c));
   EFM_LAUNCH_CHECK("gram_kernel");

@@ -37,8 +37,10 @@ def main():
 
     B, Dm, G = args.B, args.D, args.B * world
     ok = True
-    for dtype in (torch.bfloat16, torch.float32):
-        px = D.PeerExchange(B, Dm, dtype)
+    for dtype, mc in ((torch.bfloat16, None), (torch.bfloat16, False), (torch.float32, None)):
+        px = D.PeerExchange(B, Dm, dtype, multicast=mc)       # None: NVLS multicast pushes if available; False: unicast over CUDA IPC
+        if rank == 0:
+            print("exchange mode:", px.mode, dtype, flush=True)
         for s in range(args.steps):
             E, y = clustered(G, Dm, seed=100 + s)
             Eg, yg = torch.from_numpy(E).to(dev).to(dtype), torch.from_numpy(y).to(dev)
@@ -80,7 +82,7 @@ def main():
                 for _ in range(10):
                     fn()
                 e1.record(); torch.cuda.synchronize()
-                print("rank %d %s step %.1f us (B_local=%d, global %d x %d)" % (rank, name, e0.elapsed_time(e1) * 100, B, G, Dm), flush=True)
+                print("rank %d %s (%s) step %.1f us (B_local=%d, global %d x %d)" % (rank, name, px.mode, e0.elapsed_time(e1) * 100, B, G, Dm), flush=True)
         px.close()
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

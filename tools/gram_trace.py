@@ -3,7 +3,7 @@ import os, sys, json
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-trace = torch.zeros(148 * 2 * 8, dtype=torch.int64, device="cuda")
+trace = torch.zeros(148 * 2 * 16, dtype=torch.int64, device="cuda")
 os.environ["EFM_GRAM_TRACE"] = str(trace.data_ptr())
 from improving_face_recognition_performance_using_triplet_loss_b200 import _lib as L
 B, D = int(os.environ.get("KB_B", 8192)), 256
@@ -23,7 +23,7 @@ for it in range(5):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(); L.check(L.lib.efm_bh_mine(L.ptr(Et), B, 0, B, D, L.BF16, flags, L.ptr(ws), ws.numel(), L.stream())); e.record()
     torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(-1, 8).astype(np.float64)
+    t = trace.cpu().numpy().reshape(-1, 16)[:, :8].astype(np.float64)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     rel = (t - t0) / 1e3
