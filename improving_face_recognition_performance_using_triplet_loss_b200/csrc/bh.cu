@@ -78,6 +78,14 @@ template <typename T> __device__ __forceinline__ void load8(const T* p, float (&
 
 // ------------------------------------------------------------------------------------------ prep
 // One warp per row of E_all.  VEC8: D % 8 == 0 and 16-byte aligned rows -> each lane owns 8-element slabs.
+//
+// Tensor-core path (use_tc): the MINING ROWS are the raw rows rounded to bf16 (for bf16 input: the rows themselves, and
+// xm_bf16 == nullptr means "the Gram kernel reads E directly, write nothing"), zero-padded in K to a multiple of 64.  The
+// normalisation is not applied to the rows but to the Gram tile: with normalize, sq[row] receives the COLUMN SCALE
+// -1/|e_row| (mining metric: cosine, v_ij = g_ij * sq_j is monotone in the squared distance of the normalised rows for a
+// fixed anchor); without, sq[row] = |bf16(e_row)|^2 (v_ij = sq_j - 2 g_ij).  Columns beyond B_all inside the last Gram tile
+// get sq = +inf: v = +inf (plain) or 0 * inf = NaN (cosine), neither can ever be mined -- no edge path in the kernel.
+// CUDA-core fp32 path (!use_tc): normalised fp32 rows in xm_f32 (when write_f32), sq = their squared norms.
 template <typename T, bool VEC8>
 __global__ void __launch_bounds__(WARPS * 32)
 bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long B_all, int D, int Dp, int normalize,
@@ -107,15 +115,19 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
 #pragma unroll
         for (int k = 0; k < 8; ++k) ss = fmaf(v[k], v[k], ss);
         n = sqrtf(warp_sum(ss));
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = v[k] / n;
       }
       if (use_tc) {
-        union { uint4 raw; __nv_bfloat16 b[8]; } u;
+        if (xm_bf16 || !normalize) {
+          union { uint4 raw; __nv_bfloat16 b[8]; } u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { u.b[k] = __float2bfloat16_rn(v[k]); const float vb = __bfloat162float(u.b[k]); s2 = fmaf(vb, vb, s2); }
-        if (lane * 8 < Dp) *reinterpret_cast<uint4*>(xm_bf16 + row * Dp + lane * 8) = u.raw;
+          for (int k = 0; k < 8; ++k) { u.b[k] = __float2bfloat16_rn(v[k]); const float vb = __bfloat162float(u.b[k]); s2 = fmaf(vb, vb, s2); }
+          if (xm_bf16 && lane * 8 < Dp) *reinterpret_cast<uint4*>(xm_bf16 + row * Dp + lane * 8) = u.raw;
+        }
       } else {
+        if (normalize) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = v[k] / n;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) s2 = fmaf(v[k], v[k], s2);
         if (write_f32 && act) {
@@ -131,28 +143,30 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
           for (int k = 0; k < 8; ++k) ss = fmaf(v[k], v[k], ss); }
         n = sqrtf(warp_sum(ss));
       }
-      for (int d = lane * 8; d < Dp; d += 256) {
-        float v[8];
-        if (d < D) load8<T>(er + d, v);
-        else {
+      if (!use_tc || xm_bf16 || !normalize) {
+        for (int d = lane * 8; d < Dp; d += 256) {
+          float v[8];
+          if (d < D) load8<T>(er + d, v);
+          else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        }
-        if (normalize) {
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+          }
+          if (use_tc) {
+            union { uint4 raw; __nv_bfloat16 b[8]; } u;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = v[k] / n;
-        }
-        if (use_tc) {
-          union { uint4 raw; __nv_bfloat16 b[8]; } u;
+            for (int k = 0; k < 8; ++k) { u.b[k] = __float2bfloat16_rn(v[k]); const float vb = __bfloat162float(u.b[k]); s2 = fmaf(vb, vb, s2); }
+            if (xm_bf16) *reinterpret_cast<uint4*>(xm_bf16 + row * Dp + d) = u.raw;
+          } else if (d < D) {
+            if (normalize) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { u.b[k] = __float2bfloat16_rn(v[k]); const float vb = __bfloat162float(u.b[k]); s2 = fmaf(vb, vb, s2); }
-          *reinterpret_cast<uint4*>(xm_bf16 + row * Dp + d) = u.raw;
-        } else if (d < D) {
+              for (int k = 0; k < 8; ++k) v[k] = v[k] / n;
+            }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s2 = fmaf(v[k], v[k], s2);
-          if (write_f32) {
-            float4* o = reinterpret_cast<float4*>(xm_f32 + row * D + d);
-            o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            for (int k = 0; k < 8; ++k) s2 = fmaf(v[k], v[k], s2);
+            if (write_f32) {
+              float4* o = reinterpret_cast<float4*>(xm_f32 + row * D + d);
+              o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
           }
         }
       }
@@ -168,14 +182,14 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
       n = sqrtf(warp_sum(ss));
     }
     if (use_tc) {
-      __nv_bfloat16* xr = xm_bf16 + row * Dp;
-      for (int d = lane; d < Dp; d += 32) {
-        float v = 0.f;
-        if (d < D) { v = El<T>::to_f(er[d]); if (normalize) v = v / n; }
-        const __nv_bfloat16 b = __float2bfloat16_rn(v);
-        xr[d] = b;
-        const float vb = __bfloat162float(b);
-        s2 = fmaf(vb, vb, s2);
+      if (xm_bf16 || !normalize) {
+        for (int d = lane; d < Dp; d += 32) {
+          const float v = d < D ? El<T>::to_f(er[d]) : 0.f;
+          const __nv_bfloat16 b = __float2bfloat16_rn(v);
+          if (xm_bf16) xm_bf16[row * Dp + d] = b;
+          const float vb = __bfloat162float(b);
+          s2 = fmaf(vb, vb, s2);
+        }
       }
     } else {
       for (int d = lane; d < D; d += 32) {
@@ -189,12 +203,11 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
   }
   s2 = warp_sum(s2);
   if (lane == 0) {
-    sq[row] = s2;
+    sq[row] = (use_tc && normalize) ? -1.f / n : s2;
     nrm[row] = n;
     const int32_t lab = labels ? labels[row] : 0;
     if (lab_ws) {
       lab_ws[row] = lab;
-      // columns beyond B_all inside the last Gram tile: |x|^2 = +inf so they can never be mined (no edge path in the kernel)
       const long Bpad = (B_all + tc::BN - 1) / tc::BN * tc::BN;
       for (long j = B_all + row; j < Bpad; j += B_all) { sq[j] = INFINITY; lab_ws[j] = 0; }
     }
@@ -219,6 +232,7 @@ struct MineEpi {
     const int32_t* labels;    // (B_all)
     unsigned long long* kneg; // (B_local): (ord(v) << 32) | first column of the winning group of 4
     int row_offset;
+    int norm;                 // 1: cosine metric, sq holds the column scale -1/|e_j| and v_ij = g_ij * sq_j; 0: v_ij = sq_j - 2 g_ij
   };
   struct State {
     int lab_i;
@@ -248,15 +262,29 @@ struct MineEpi {
     const float4* sq4 = reinterpret_cast<const float4*>(tile + (bc & 3) * 16);
     const int4* lb4 = reinterpret_cast<const int4*>(tile + 64 + (bc & 3) * 16);
     float pm[4];                                     // group-of-4 minima
+    if (p.norm) {                                    // warp-uniform
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 s4 = sq4[q];
-      const int4 l4 = lb4[q];
-      const float v0 = fmaf(-2.f, __uint_as_float(acc[4 * q + 0]), (l4.x == s.lab_i) ? INFINITY : s4.x);
-      const float v1 = fmaf(-2.f, __uint_as_float(acc[4 * q + 1]), (l4.y == s.lab_i) ? INFINITY : s4.y);
-      const float v2 = fmaf(-2.f, __uint_as_float(acc[4 * q + 2]), (l4.z == s.lab_i) ? INFINITY : s4.z);
-      const float v3 = fmaf(-2.f, __uint_as_float(acc[4 * q + 3]), (l4.w == s.lab_i) ? INFINITY : s4.w);
-      pm[q] = fminf(fminf(fminf(v0, v1), v2), v3);                   // FMNMX3 + FMNMX
+      for (int q = 0; q < 4; ++q) {
+        const float4 s4 = sq4[q];
+        const int4 l4 = lb4[q];
+        // padding columns: g = 0, scale = +inf -> NaN, which fminf drops
+        const float v0 = (l4.x == s.lab_i) ? INFINITY : __uint_as_float(acc[4 * q + 0]) * s4.x;
+        const float v1 = (l4.y == s.lab_i) ? INFINITY : __uint_as_float(acc[4 * q + 1]) * s4.y;
+        const float v2 = (l4.z == s.lab_i) ? INFINITY : __uint_as_float(acc[4 * q + 2]) * s4.z;
+        const float v3 = (l4.w == s.lab_i) ? INFINITY : __uint_as_float(acc[4 * q + 3]) * s4.w;
+        pm[q] = fminf(fminf(fminf(v0, v1), v2), v3);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 s4 = sq4[q];
+        const int4 l4 = lb4[q];
+        const float v0 = fmaf(-2.f, __uint_as_float(acc[4 * q + 0]), (l4.x == s.lab_i) ? INFINITY : s4.x);
+        const float v1 = fmaf(-2.f, __uint_as_float(acc[4 * q + 1]), (l4.y == s.lab_i) ? INFINITY : s4.y);
+        const float v2 = fmaf(-2.f, __uint_as_float(acc[4 * q + 2]), (l4.z == s.lab_i) ? INFINITY : s4.z);
+        const float v3 = fmaf(-2.f, __uint_as_float(acc[4 * q + 3]), (l4.w == s.lab_i) ? INFINITY : s4.w);
+        pm[q] = fminf(fminf(fminf(v0, v1), v2), v3);                 // FMNMX3 + FMNMX
+      }
     }
     const float m = fminf(fminf(fminf(pm[0], pm[1]), pm[2]), pm[3]);
     if (m < s.nbest) {                               // strict: the earlier group survives ties
@@ -367,17 +395,24 @@ struct DistFin {
   int32_t* rip; int32_t* rin; float* rw;        // (B_all) result arrays of this step in the own region, indexed by global row
   unsigned long long* sig[tc::MAX_PEERS];       // rank r's arrival counter for THIS rank's results
 };
-// squared distance between two bf16 mining rows, warp-cooperative, fp32 direct differences
-__device__ __forceinline__ float xm_dist(const __nv_bfloat16* a, const __nv_bfloat16* b, int Dp, int lane) {
+// "how far is mining row b from mining row a", warp-cooperative, fp32 on the bf16 mining rows: squared distance by direct
+// differences (plain), or -(a . b) / |e_b| (cosine metric: `scale_b` = -1/|e_b|; the anchor's own norm is a common factor)
+__device__ __forceinline__ float xm_far(const __nv_bfloat16* a, const __nv_bfloat16* b, int Dp, int lane, int normalize, float scale_b) {
   float s = 0.f;
   for (int d = lane * 8; d < Dp; d += 256) {
     float x[8], y[8];
     load8<__nv_bfloat16>(a + d, x);
     load8<__nv_bfloat16>(b + d, y);
+    if (normalize) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { const float t = x[k] - y[k]; s = fmaf(t, t, s); }
+      for (int k = 0; k < 8; ++k) s = fmaf(x[k], y[k], s);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float t = x[k] - y[k]; s = fmaf(t, t, s); }
+    }
   }
-  return warp_sum(s);
+  s = warp_sum(s);
+  return normalize ? s * scale_b : s;
 }
 
 // One warp per anchor.  mode 0: kpos/kneg hold exact indices (fp32 mining kernel).  mode 1 (tensor-core path):
@@ -388,7 +423,7 @@ __global__ void __launch_bounds__(WARPS * 32, 6)
 bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int normalize, long B_all, int D,
                    long row_offset, long B_local, float margin, const float* __restrict__ head_grad, int detach,
                    int mode, const unsigned long long* __restrict__ kpos, const unsigned long long* __restrict__ kneg,
-                   const __nv_bfloat16* __restrict__ xm, int Dp, const int32_t* __restrict__ lab,
+                   const __nv_bfloat16* __restrict__ xm, int Dp, const float* __restrict__ cs, const int32_t* __restrict__ lab,
                    const int32_t* __restrict__ hcnt, const int32_t* __restrict__ hmem,
                    const int32_t* __restrict__ hhead, const int32_t* __restrict__ hnext,
                    const int32_t* __restrict__ hslot, float* __restrict__ loss, int32_t* __restrict__ idx_p,
@@ -397,7 +432,7 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
                    const DistFin df) {
   pdl_trigger();
   pdl_wait();                                                        // the mining kernel has completed
-  if (df.world > 1) {                                                // the peers' original rows must have landed
+  if (df.world > 1 && df.wait_b) {                                   // the peers' original rows (stage B) must have landed
     if ((int)threadIdx.x < df.world) tc::wait_counter_thread(df.wait_b + threadIdx.x, df.target_b);
     __syncthreads();
   }
@@ -439,20 +474,34 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     { unsigned m = vmask; for (int k = 0; k < slot && m; ++k) m &= m - 1; if (m && slot < ncand) src = __ffs(m) - 1; }
     const int cand = __shfl_sync(0xffffffffu, mine, src < 0 ? 0 : src);
     const bool is_pos = src >= 0 && src < 8;
-    float d = 0.f;
+    // "how far" score of the candidate: squared distance of the mining rows (plain) or -(x_i . x_c) / |e_c| (cosine metric:
+    // cs = -1/|e|, the anchor's norm is a common positive factor) -- larger = farther in both cases
+    float d = 0.f, csc = 1.f;
     if (src >= 0) {
       const __nv_bfloat16* xc = xm + (long)cand * Dp;
+      if (normalize) csc = cs[cand];
       // the lanes of one candidate read adjacent 16-byte pieces: every 32-byte sector is requested once
-      for (int e = part * 8; e < Dp; e += lanes_per * 8) {
-        float x[8], y[8];
-        load8<__nv_bfloat16>(xi + e, x);
-        load8<__nv_bfloat16>(xc + e, y);
+      if (normalize) {
+        for (int e = part * 8; e < Dp; e += lanes_per * 8) {
+          float x[8], y[8];
+          load8<__nv_bfloat16>(xi + e, x);
+          load8<__nv_bfloat16>(xc + e, y);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const float t = x[k] - y[k]; d = fmaf(t, t, d); }
+          for (int k = 0; k < 8; ++k) d = fmaf(x[k], y[k], d);
+        }
+      } else {
+        for (int e = part * 8; e < Dp; e += lanes_per * 8) {
+          float x[8], y[8];
+          load8<__nv_bfloat16>(xi + e, x);
+          load8<__nv_bfloat16>(xc + e, y);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float t = x[k] - y[k]; d = fmaf(t, t, d); }
+        }
       }
     }
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) { const float od = __shfl_xor_sync(0xffffffffu, d, o); if (o < lanes_per) d += od; }
+    if (normalize) d *= csc;
     // hardest positive: max d (lowest index on ties); hardest negative: min d (lowest index on ties)
     float pd = (src >= 0 && is_pos) ? d : -INFINITY; int pi = (src >= 0 && is_pos) ? cand : -1;
     float nd = (src >= 0 && !is_pos) ? d : INFINITY; int ni = (src >= 0 && !is_pos) ? cand : -1;
@@ -467,7 +516,7 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     if (cnt > 8) {                                                   // rare: labels with more than 8 rows
       for (int j = hhead[sl]; j >= 0; j = hnext[j]) {
         if (j == gi) continue;
-        const float dj = xm_dist(xi, xm + (long)j * Dp, Dp, lane);
+        const float dj = xm_far(xi, xm + (long)j * Dp, Dp, lane, normalize, normalize ? cs[j] : 1.f);
         if (ip < 0 || dj > pd || (dj == pd && j < ip)) { pd = dj; ip = j; }
       }
     }
@@ -665,13 +714,20 @@ extern "C" int efm_bh_profile_events(void* const* events, int n) {
     if ((i) < g_prof_n && g_prof_ev[i]) EFM_CUDA(cudaEventRecord(g_prof_ev[i], (st))); \
   } while (0)
 
+// The bf16 mining rows of the tensor-core path: the caller's rows themselves when they already are bf16 with K a multiple
+// of 64 (nothing is copied), else the rounded / zero-padded copy bh_prep writes into the workspace.
+static bool bh_mine_in_place(const BhLayout& L, const void* E_all, long D, int dtype) {
+  return L.use_tc && dtype == EFM_BF16 && D == L.Dp && aligned(E_all, 16);
+}
+
 static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, long B_all, long row_offset, long B_local,
-                            long D, cudaStream_t st, bool pdl = false) {
+                            long D, int dtype, int normalize, cudaStream_t st, bool pdl = false) {
   auto* kpos = reinterpret_cast<unsigned long long*>(ws + L.kpos);
   auto* kneg = reinterpret_cast<unsigned long long*>(ws + L.kneg);
   float* sq = reinterpret_cast<float*>(ws + L.sq);
   int32_t* lab = reinterpret_cast<int32_t*>(ws + L.lab);
-  auto* xm_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + L.xm);
+  const auto* xm_bf16 = bh_mine_in_place(L, E_all, D, dtype) ? static_cast<const __nv_bfloat16*>(E_all)
+                                                              : reinterpret_cast<const __nv_bfloat16*>(ws + L.xm);
   float* xm_f32 = reinterpret_cast<float*>(ws + L.xm);
   if (L.use_tc) {
     tc::GramParams g{};
@@ -683,7 +739,7 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
       if (ph > 1 && ct % ph == 0) { g.phases = ph; g.phase0 = (int)((row_offset * ph) / B_all) % ph; }
     }
     const int grid = tc::plan_gram(g, mh, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, cg);
-    MineEpi::Params ep{sq, lab, kneg, (int)row_offset};
+    MineEpi::Params ep{sq, lab, kneg, (int)row_offset, normalize};
     return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st, cg, pdl);
   }
   const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
@@ -755,22 +811,24 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
 
   EFM_BH_STAGE(0, st);
   EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));     // empty label table + empty chains
+  const bool in_place = bh_mine_in_place(L, E_all, D, dtype);
+  const __nv_bfloat16* xm_rows = in_place ? static_cast<const __nv_bfloat16*>(E_all) : xm_bf16;
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, labels_all, B_all, (int)D, L.Dp, normalize,
                                                           L.use_tc ? 1 : 0, L.xm_f32 ? 1 : 0, row_offset, B_local, sq, nrm,
-                                                          lab, xm_bf16, xm_f32, kpos, kneg, nullptr, hkeys, hcnt, hmem,
-                                                          hhead, hnext, hslot, L.tbits);
+                                                          lab, in_place ? nullptr : xm_bf16, xm_f32, kpos, kneg, nullptr, hkeys,
+                                                          hcnt, hmem, hhead, hnext, hslot, L.tbits);
   });
   EFM_LAUNCH_CHECK("bh_prep");
   EFM_BH_STAGE(1, st);
   {
-    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, st, true);
+    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, dtype, normalize, st, true);
     if (rc) return rc;
   }
   EFM_BH_STAGE(2, st);
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     EFM_LAUNCH((bh_finalize_kernel<T, V>), grid_loc, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
-               B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos, kneg, xm_bf16, L.Dp, lab, hcnt, hmem, hhead, hnext, hslot,
+               B_local, margin, head_grad, detach, L.use_tc ? 1 : 0, kpos, kneg, xm_rows, L.Dp, sq, lab, hcnt, hmem, hhead, hnext, hslot,
                loss, idx_p, idx_n, wgt, rheadp, rheadn, rnextp, rnextn, DistFin{});
   });
   EFM_LAUNCH_CHECK("bh_finalize");
@@ -836,7 +894,7 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
     EFM_BH_DISPATCH(dtype, vec, T, V, {
       bh_finalize_kernel<T, V><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_all, nrm, normalize, B_all, (int)D, row_offset,
                                                                 B_local, margin, head_grad, detach, 2, nullptr, nullptr, nullptr,
-                                                                0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                 const_cast<int32_t*>(idx_p), const_cast<int32_t*>(idx_n), wgt,
                                                                 rheadp, rheadn, rnextp, rnextn, DistFin{});
     });
@@ -968,8 +1026,8 @@ extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long 
   EFM_REQUIRE(E_all && workspace && aligned(workspace, 256), EFM_E_ARG, "efm_bh_mine: bad pointer");
   const BhLayout L = bh_layout(B_local, B_all, D, dtype, flags);
   EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_mine: workspace too small");
-  return bh_launch_mining(L, E_all, static_cast<uint8_t*>(workspace), B_all, row_offset, B_local, D,
-                          static_cast<cudaStream_t>(stream));
+  return bh_launch_mining(L, E_all, static_cast<uint8_t*>(workspace), B_all, row_offset, B_local, D, dtype,
+                          (flags & EFM_BH_NORMALIZE) ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 // ============================================================================================================
@@ -1001,7 +1059,7 @@ extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long 
 namespace efm {
 namespace {
 
-struct XchgLayout { int Dp; size_t cnt_a, cnt_b, cnt_c, buf0, buf_bytes, xm, sq, lab, nrm, E, rip, rin, rw, total; };
+struct XchgLayout { int Dp; bool e_is_xm; size_t cnt_a, cnt_b, cnt_c, buf0, buf_bytes, xm, sq, lab, nrm, E, rip, rin, rw, total; };
 XchgLayout xchg_layout(long B, int world, long D, int dtype) {
   XchgLayout L{};
   L.Dp = (int)(cdiv(D, tc::BK) * tc::BK);
@@ -1011,7 +1069,10 @@ XchgLayout xchg_layout(long B, int world, long D, int dtype) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.xm = take(B_all * L.Dp * 2);
   L.sq = take(B_all * 4); L.lab = take(B_all * 4); L.nrm = take(B_all * 4);
-  L.E = take(B_all * D * dtype_size(dtype));
+  // bf16 rows with K a multiple of 64 ARE their own mining rows: one array serves the Gram kernel, finalize and gradient,
+  // and there is no stage B.  Other dtypes / widths: the original rows travel as stage B next to the bf16 mining rows.
+  L.e_is_xm = dtype == EFM_BF16 && D == L.Dp;
+  L.E = take(L.e_is_xm ? 0 : B_all * D * dtype_size(dtype));
   L.rip = take(B_all * 4); L.rin = take(B_all * 4); L.rw = take(B_all * 4);
   L.buf_bytes = off;
   L.total = L.buf0 + 2 * L.buf_bytes;
@@ -1121,7 +1182,7 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
   float* sq = reinterpret_cast<float*>(buf + X.sq);
   int32_t* lab = reinterpret_cast<int32_t*>(buf + X.lab);
   float* nrm = reinterpret_cast<float*>(buf + X.nrm);
-  const void* E_all = buf + X.E;
+  const void* E_all = X.e_is_xm ? static_cast<const void*>(xm) : static_cast<const void*>(buf + X.E);
   int32_t* rip = reinterpret_cast<int32_t*>(buf + X.rip);
   int32_t* rin = reinterpret_cast<int32_t*>(buf + X.rin);
   float* rw = reinterpret_cast<float*>(buf + X.rw);
@@ -1167,7 +1228,7 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
     g.ready = reinterpret_cast<const unsigned long long*>(own + X.cnt_a);
     g.ready_target = target_ab;
     tc::CommParams cp{};
-    cp.world = world; cp.rank = rank; cp.nseg_a = 4; cp.nseg = 5; cp.self_b = 1;
+    cp.world = world; cp.rank = rank; cp.nseg_a = 4; cp.nseg = X.e_is_xm ? 4 : 5; cp.self_b = X.e_is_xm ? 0 : 1;
     for (int r = 0; r < world; ++r) cp.peer[r] = static_cast<uint8_t*>(regions[r]);
     cp.mc = world > 1 ? static_cast<uint8_t*>(mc_region) : nullptr;
     cp.seg[0] = {reinterpret_cast<const uint8_t*>(xm + row0 * X.Dp), boff + X.xm + (size_t)row0 * X.Dp * 2, (unsigned long long)B * X.Dp * 2};
@@ -1178,7 +1239,7 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
     cp.cnt_a_off = X.cnt_a; cp.cnt_b_off = X.cnt_b;
     cp.tab_lab = lab; cp.tab_rows = B_all;                               // label table of the global batch, built by the same warps
     cp.hkeys = hkeys; cp.hcnt = hcnt; cp.hmem = hmem; cp.hhead = hhead; cp.hnext = hnext; cp.hslot = hslot; cp.tbits = L.tbits;
-    MineEpi::Params ep{sq, lab, kneg, (int)row0};
+    MineEpi::Params ep{sq, lab, kneg, (int)row0, normalize};
     const int rc = tc::launch_gram_mh<MineEpi, 1, 2, true>(xm + row0 * X.Dp, xm, g, ep, grid, st, &cp, true);
     if (rc) return rc;
   }
@@ -1186,14 +1247,15 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
   // 3. finalize the local anchors (waits for stage B: the original rows of every rank, own copy included)
   DistFin df{};
   df.world = world; df.rank = rank;
-  df.wait_b = reinterpret_cast<const unsigned long long*>(own + X.cnt_b); df.target_b = target_ab;
+  df.wait_b = X.e_is_xm ? nullptr : reinterpret_cast<const unsigned long long*>(own + X.cnt_b);
+  df.target_b = target_ab;
   df.rip = rip; df.rin = rin; df.rw = rw;                                // published in every mode, so the result counters of all
   for (int r = 0; r < world; ++r)                                        // ranks advance in lockstep whatever mix of flags is used
     df.sig[r] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(regions[r]) + X.cnt_c) + rank;
   const bool chains_local = dE_local && !exact;
   EFM_DISPATCH_DTYPE(dtype, T, {
     EFM_LAUNCH((bh_finalize_kernel<T, true>), grid_loc, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B_all, (int)D, row0, B,
-               margin, head_grad, chains_local ? 1 : 0, 1, kpos, kneg, xm, X.Dp, lab, hcnt, hmem, hhead, hnext, hslot, loss, idx_p,
+               margin, head_grad, chains_local ? 1 : 0, 1, kpos, kneg, xm, X.Dp, sq, lab, hcnt, hmem, hhead, hnext, hslot, loss, idx_p,
                idx_n, chains_local ? wgt : nullptr, chains_local ? rheadp : nullptr, rheadn, rnextp, rnextn, df);
   });
   EFM_LAUNCH_CHECK("bh_finalize(dist)");

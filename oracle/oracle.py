@@ -148,8 +148,11 @@ def batch_hard_triplet(E, labels, margin, normalize=True, E_all=None, labels_all
     [row_offset, row_offset+B) are E).  Returns dict(loss, idx_p, idx_n, dE_all) where
     dE_all has E_all's shape (roles anchor/positive/negative all receive gradient,
     i.e. the exact single-GPU-equivalent form of SURVEY 8e).
-    mine_bf16: the mining Gram is evaluated on bf16-rounded (normalised) rows, the loss
-    and gradient on the fp32 rows -- the contract of the tensor-core path."""
+    mine_bf16: the contract of the tensor-core path -- the MINING rows are the raw rows rounded to
+    bf16 (bf16 inputs: the rows themselves); with normalize the mining metric is the cosine of the
+    mining rows, (xm_i . xm_j) / (|e_i| |e_j|) with the norms of the original rows (hardest positive =
+    smallest cosine, hardest negative = largest; the same ordering as the squared distance of the
+    normalised rows), without it their squared distance.  Loss and gradient use the fp32 rows."""
     E = np.asarray(E, dtype=np.float64)
     if E_all is None:
         E_all, labels_all = E, labels
@@ -162,11 +165,15 @@ def batch_hard_triplet(E, labels, margin, normalize=True, E_all=None, labels_all
     B = E.shape[0]
     X = X_all[row_offset:row_offset + B]
     if mine_bf16:
-        Xm_all = bf16_round(X_all.astype(F32)).astype(np.float64)
+        Xm_all = bf16_round(E_all.astype(F32)).astype(np.float64)
         Xm = Xm_all[row_offset:row_offset + B]
+        if normalize:
+            cos = (Xm @ Xm_all.T) / (nrm_all[row_offset:row_offset + B] * nrm_all.reshape(1, -1))
+            idx_p, idx_n = batch_hard_mine(Xm, labels, Xm_all, labels_all, row_offset, dist=-cos)
+        else:
+            idx_p, idx_n = batch_hard_mine(Xm, labels, Xm_all, labels_all, row_offset)
     else:
-        Xm_all, Xm = X_all, X
-    idx_p, idx_n = batch_hard_mine(Xm, labels, Xm_all, labels_all, row_offset)
+        idx_p, idx_n = batch_hard_mine(X, labels, X_all, labels_all, row_offset)
     valid = (idx_p >= 0) & (idx_n >= 0)
     ip = np.where(valid, idx_p, 0); inn = np.where(valid, idx_n, 0)
     P = X_all[ip]; Nn = X_all[inn]

@@ -413,12 +413,13 @@ def test_bh_full_size_properties(P):
     assert (loss > 0).sum() > 1024
     ip, inn = ip.cpu().numpy(), inn.cpu().numpy()
     assert (y[ip] == y).all() and (ip != np.arange(8192)).all() and (y[inn] != y).all()
-    # the mined pair must be at least as hard as 64 random candidates of the right kind (bf16-rounded rows)
-    X = O.l2norm_fwd(Et.float().cpu().numpy())[0]; Xm = O.bf16_round(X).astype(np.float64)
+    # the mined pair must be the hardest of ALL candidates of the right kind under the mining metric: cosine of the bf16
+    # rows with fp32 norms (d = -cos, larger = farther)
+    Xm = Et.float().cpu().numpy().astype(np.float64); nr = np.sqrt((Xm * Xm).sum(1))
     rng = np.random.default_rng(0)
     rows = rng.integers(0, 8192, 256)
     for i in rows:
-        d = ((Xm[i] - Xm) ** 2).sum(1)
+        d = -(Xm @ Xm[i]) / (nr * nr[i])
         same = y == y[i]; same[i] = False
         assert d[ip[i]] >= d[same].max() - 1e-5 and d[inn[i]] <= d[y != y[i]].min() + 1e-5
         assert ip[i] == np.flatnonzero(same)[np.argmax(d[same])] and inn[i] == np.flatnonzero(y != y[i])[np.argmin(d[y != y[i]])]
