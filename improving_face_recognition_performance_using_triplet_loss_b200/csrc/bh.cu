@@ -387,13 +387,15 @@ bh_mine_f32_kernel(const float* __restrict__ X, const float* __restrict__ sq, co
 // ------------------------------------------------------------------------------------------ finalize
 // Multi-GPU step (see efm_bh_dist_fwd_bwd): what bh_finalize waits for, where it publishes an anchor's mining result and
 // whom it tells.  Results stay in LOCAL memory (this rank's exchange region, where the peers' chain kernels read them over
-// NVLink): the only remote traffic of the kernel is one release-add per block on every peer's arrival counter.
+// NVLink): the kernel itself causes no remote traffic at all.
 struct DistFin {
   int world, rank;                              // world = 0: single-GPU call, nothing of this applies
   const unsigned long long* wait_b;             // [world] local arrival counters of exchange stage B (the original rows read below)
   unsigned long long target_b;
   int32_t* rip; int32_t* rin; float* rw;        // (B_all) result arrays of this step in the own region, indexed by global row
-  unsigned long long* sig[tc::MAX_PEERS];       // rank r's arrival counter for THIS rank's results
+  unsigned long long* done;                     // LOCAL counter in the own region: +1 per finished block; the peers' chain kernels
+                                                // poll it over NVLink (a system-scope fence + remote atomic per block costs tens of
+                                                // microseconds per block while the links are busy)
 };
 // "how far is mining row b from mining row a", warp-cooperative, fp32 on the bf16 mining rows: squared distance by direct
 // differences (plain), or -(a . b) / |e_b| (cosine metric: `scale_b` = -1/|e_b|; the anchor's own norm is a common factor)
@@ -567,12 +569,10 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
     if (df.world > 0) { df.rip[gi] = ip; df.rin[gi] = in; df.rw[gi] = w2; }
   }
   }
-  if (df.world > 1) {                                              // one arrival per block on every peer's counter
+  if (df.world > 1) {                                              // results of this block are in L2: count the block as done
     __threadfence();
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < tc::MAX_PEERS; ++r)                       // static indices: the parameter array stays in constant memory
-      if ((int)threadIdx.x == r && r < df.world && r != df.rank) tc::red_release_sys_add_u64(df.sig[r], 1ull);
+    if (threadIdx.x == 0) atomicAdd(df.done, 1ull);
   }
 }
 
@@ -921,8 +921,10 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
 struct ChainPull {
   int world, rank;
   long rows_per_rank;
-  const unsigned long long* cnt;                // [world] local arrival counters
-  unsigned long long target;
+  const unsigned long long* done[tc::MAX_PEERS];   // rank r's finalize-completion counter (in r's region, read over NVLink)
+  unsigned long long target;                    // its value once r's finalize of this step has finished
+  unsigned long long* gate;                     // local: set to `step` by block 0 once every peer is done
+  unsigned long long step;
   const int32_t* ip[tc::MAX_PEERS]; const int32_t* in[tc::MAX_PEERS]; const float* w[tc::MAX_PEERS];   // rank r's arrays as mapped here
 };
 __global__ void __launch_bounds__(256)
@@ -932,14 +934,33 @@ bh_chain_kernel(int32_t* idx_p, int32_t* idx_n, float* wgt,
   pdl_trigger();
   pdl_wait();
   if (pull.world > 1) {
-    if ((int)threadIdx.x < pull.world && (int)threadIdx.x != pull.rank) tc::wait_counter_thread(pull.cnt + threadIdx.x, pull.target);
-    __syncthreads();
+    // Block 0 polls the peers' completion counters over NVLink (world - 1 threads, not world - 1 per block) and opens a local
+    // gate; every other block spins on the gate in local L2.  Block 0 is dispatched first, so the gate always opens.
+    if (blockIdx.x == 0) {
+#pragma unroll
+      for (int r = 0; r < tc::MAX_PEERS; ++r)
+        if ((int)threadIdx.x == r && r < pull.world && r != pull.rank) tc::wait_counter_thread(pull.done[r], pull.target);
+      __syncthreads();
+      if (threadIdx.x == 0) { __threadfence(); atomicMax(pull.gate, pull.step); }
+    } else {
+      if (threadIdx.x == 0) {
+        const unsigned long long t0 = tc::gtimer();
+        while (*reinterpret_cast<volatile unsigned long long*>(pull.gate) < pull.step) {
+          __nanosleep(100);
+          if (tc::gtimer() - t0 > 8000000000ull) tc::peer_timeout(pull.gate, 0ull, pull.step);
+        }
+        __threadfence();
+      }
+      __syncthreads();
+    }
     const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n_anchors) {
       const int owner = (int)(j / pull.rows_per_rank);
       if (owner != pull.rank) {
-        const int p = __ldcg(pull.ip[owner] + j), n = __ldcg(pull.in[owner] + j);
-        const float w = __ldcg(pull.w[owner] + j);
+        int p = 0, n = 0; float w = 0.f;
+#pragma unroll
+        for (int r = 0; r < tc::MAX_PEERS; ++r)                         // static indices: the pointer arrays stay in constant memory
+          if (r == owner) { p = __ldcg(pull.ip[r] + j); n = __ldcg(pull.in[r] + j); w = __ldcg(pull.w[r] + j); }
         idx_p[j] = p; idx_n[j] = n; wgt[j] = w;
         if (w != 0.f) {
           const long pl = p - row_begin, nl = n - row_begin;
@@ -1064,7 +1085,7 @@ XchgLayout xchg_layout(long B, int world, long D, int dtype) {
   XchgLayout L{};
   L.Dp = (int)(cdiv(D, tc::BK) * tc::BK);
   const size_t B_all = (size_t)B * world;
-  L.cnt_a = 0; L.cnt_b = 64; L.cnt_c = 128; L.buf0 = 256;
+  L.cnt_a = 0; L.cnt_b = 64; L.cnt_c = 128; L.buf0 = 256;              // cnt_c: [0] finalize-completion counter, [1] chain gate
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.xm = take(B_all * L.Dp * 2);
@@ -1249,9 +1270,8 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
   df.world = world; df.rank = rank;
   df.wait_b = X.e_is_xm ? nullptr : reinterpret_cast<const unsigned long long*>(own + X.cnt_b);
   df.target_b = target_ab;
-  df.rip = rip; df.rin = rin; df.rw = rw;                                // published in every mode, so the result counters of all
-  for (int r = 0; r < world; ++r)                                        // ranks advance in lockstep whatever mix of flags is used
-    df.sig[r] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(regions[r]) + X.cnt_c) + rank;
+  df.rip = rip; df.rin = rin; df.rw = rw;                                // published in every mode, so the completion counters of
+  df.done = reinterpret_cast<unsigned long long*>(own + X.cnt_c);        // all ranks advance in lockstep whatever mix of flags is used
   const bool chains_local = dE_local && !exact;
   EFM_DISPATCH_DTYPE(dtype, T, {
     EFM_LAUNCH((bh_finalize_kernel<T, true>), grid_loc, WARPS * 32, 0, st, true, (const T*)E_all, nrm, normalize, B_all, (int)D, row0, B,
@@ -1265,9 +1285,11 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
   if (exact) {
     ChainPull pull{};
     pull.world = world; pull.rank = rank; pull.rows_per_rank = B;
-    pull.cnt = reinterpret_cast<const unsigned long long*>(own + X.cnt_c);
-    pull.target = step * (unsigned long long)grid_loc;                   // one arrival per finalize block of the owner per step
+    pull.target = step * (unsigned long long)grid_loc;                   // one count per finalize block of the owner per step
+    pull.gate = reinterpret_cast<unsigned long long*>(own + X.cnt_c) + 1;
+    pull.step = step;
     for (int r = 0; r < world; ++r) {
+      pull.done[r] = reinterpret_cast<const unsigned long long*>(static_cast<const uint8_t*>(regions[r]) + X.cnt_c);
       const uint8_t* b = static_cast<const uint8_t*>(regions[r]) + boff;
       pull.ip[r] = reinterpret_cast<const int32_t*>(b + X.rip); pull.in[r] = reinterpret_cast<const int32_t*>(b + X.rin);
       pull.w[r] = reinterpret_cast<const float*>(b + X.rw);

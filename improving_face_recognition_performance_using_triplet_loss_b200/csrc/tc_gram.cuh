@@ -221,6 +221,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ void red_release_sys_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_sys_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// acquire-release fence at system scope (MEMBAR.ALL.SYS): cheaper than __threadfence_system(), which is a
+// sequentially-consistent fence (MEMBAR.SC.SYS)
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 static __device__ __noinline__ void peer_timeout(const void* p, unsigned long long have, unsigned long long want) {
   printf("efmtl: peer wait timeout block %d thread %d counter %p = %llu < %llu\n", blockIdx.x, threadIdx.x, p, have, want);
   __trap();
@@ -230,10 +241,11 @@ __device__ __forceinline__ void wait_counter_thread(const unsigned long long* p,
   unsigned long long v = ld_acquire_sys_u64(p);
   if (v < target) {
     const unsigned long long t0 = gtimer();
-    while ((v = ld_acquire_sys_u64(p)) < target) {
+    while ((v = ld_relaxed_sys_u64(p)) < target) {                           // relaxed polls ...
       __nanosleep(200);
       if (gtimer() - t0 > 8000000000ull) peer_timeout(p, v, target);         // 8 s
     }
+    (void)ld_acquire_sys_u64(p);                                             // ... one acquire once the value is there
   }
 }
 // Whole warp calls; lane 0 polls, the rest of the warp is ordered behind it by the warp barrier.
@@ -293,7 +305,7 @@ __device__ __forceinline__ void comm_push_mc(const CommParams& cp, int part, int
     if (s0 == s1) continue;
     for (int s = s0; s < s1; ++s) push_share_mc(cp.mc + cp.seg[s].dst_off, cp.seg[s].src, cp.seg[s].bytes, part, nparts, lane);
     const unsigned long long tf = trace ? gtimer() : 0ull;
-    __threadfence_system();
+    fence_acq_rel_sys();
     __syncwarp();
     if (lane == 0) {
       multimem_red_release_add_u64(cp.mc + (stage ? cp.cnt_b_off : cp.cnt_a_off) + 8ull * cp.rank, 1ull);
@@ -316,10 +328,10 @@ __device__ __forceinline__ void comm_push(const CommParams& cp, int part, int np
       uint8_t* base = cp.peer[dest];
       for (int s = s0; s < s1; ++s) push_share(base + cp.seg[s].dst_off, cp.seg[s].src, cp.seg[s].bytes, part, nparts, lane);
       const unsigned long long tf = trace ? gtimer() : 0ull;
-      __threadfence_system();
+      fence_acq_rel_sys();                                           // the whole warp: its stores have been performed at the peer
       __syncwarp();
       if (lane == 0) {
-        red_release_sys_add_u64(reinterpret_cast<unsigned long long*>(base + (stage ? cp.cnt_b_off : cp.cnt_a_off)) + cp.rank, 1ull);
+        red_relaxed_sys_add_u64(reinterpret_cast<unsigned long long*>(base + (stage ? cp.cnt_b_off : cp.cnt_a_off)) + cp.rank, 1ull);
         if (trace) trace[15] += gtimer() - tf;                       // time spent in fences
       }
     }
