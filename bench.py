@@ -8,8 +8,8 @@ Workload at N=1: BASELINE config C2 -- batch-hard triplet loss forward+backward,
 embeddings (2048 identities x 4), margin 0.2, per-row L2 normalisation with backward, on one B200.
 N>1: BASELINE config C3 -- global batch 65,536 x 256 (16,384 identities x 4) split over the N GPUs
 (65,536/N anchors per rank mined against the whole global batch; "strong" scaling: total work fixed).
-The step is the FUSED multi-GPU step (efm_bh_dist_fwd_bwd): no NCCL call -- the Gram + mining kernel pushes
-the rank's rows into the peers' exchange regions over NVLink while it mines the blocks that have already
+The step is the FUSED multi-GPU step (efm_bh_dist_fwd_bwd): no NCCL call -- extra warps of the Gram + mining kernel copy
+the peers' rows over NVLink while the tensor pipeline mines the blocks that have already
 arrived; exact gradient (12 bytes per anchor published to every rank, no dense reduce-scatter).  The line
 also carries `c3_single_gpu_ms_per_step` (the same 65,536-row job on rank 0 alone, measured in the same run)
 and `speedup_vs_single_gpu`.  `--workload c3-nccl` runs the NCCL all-gather form, `--workload c3-weak`
@@ -225,7 +225,7 @@ def run_ours(args):
     fused = world > 1 and name == "c3"
     if fused:
         try:
-            px = D.PeerExchange(B, DIM, torch.bfloat16, device=dev, multicast={"auto": None, "on": True, "off": False}[args.multicast])
+            px = D.PeerExchange(B, DIM, torch.bfloat16, device=dev)
         except Exception as e:  # noqa: BLE001  (no peer access / IPC on this box: say so and use the NCCL form)
             if rank == 0:
                 print("bench: fused exchange unavailable (%s); using the NCCL all-gather form" % e, file=sys.stderr, flush=True)
@@ -243,7 +243,7 @@ def run_ours(args):
         def step():
             px.steps += 1
             L.check(L.lib.efm_bh_dist_fwd_bwd(L.ptr(E_loc), L.ptr(y_loc), B, DIM, dt, MARGIN, None, flags, world, rank, px.regions,
-                                              px.mc, px.steps, L.ptr(loss), L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE_loc), L.ptr(px.ws),
+                                              px.steps, L.ptr(loss), L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE_loc), L.ptr(px.ws),
                                               px.ws.numel(), L.stream()))
     else:
         ws = L.workspace(L.lib.efm_bh_workspace_bytes(B, G, DIM, dt, flags), dev)
@@ -415,9 +415,9 @@ def run_ours(args):
         achieved = flops / (t_kernel * 1e-3) / 1e12
         peak = float(pk["bf16_tflops"])                                # burst figure: kernel timed alone
         if fused:
-            par = "dp%d, exchange fused into the Gram kernel over NVLink peer memory (%s; no NCCL); exact gradient via 12 B/anchor" % (
-                world, xmode)
-            kname = "gram_kernel<MineEpi,COMM> (tcgen05 Gram + mining epilogue + NVLink push/arrival waits), timed inside the step"
+            par = "dp%d, exchange fused into the Gram kernel (peer rows copied over NVLink by extra warps, %s; no NCCL); exact " \
+                  "gradient via 12 B/anchor fetched from the owners" % (world, xmode)
+            kname = "gram_kernel<MineEpi,COMM> (tcgen05 Gram + mining epilogue + NVLink peer copies), timed inside the step"
         elif world > 1:
             par = "dp%d NCCL all-gather fwd / reduce-scatter bwd" % world
             kname = "gram_kernel<MineEpi> (tcgen05 Gram + batch-hard mining epilogue)"
@@ -470,7 +470,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c3-strong", "c3-nccl", "c3-weak"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"], help="N > 1: NVLS multicast pushes (auto = if available)")
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same C3 job")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -58,7 +58,7 @@ SIGNATURES = {
     "efm_ipc_export": (_i, [_vp, C.c_char_p]),
     "efm_ipc_import": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "efm_ipc_release": (_i, [_vp]),
-    "efm_bh_dist_fwd_bwd": (_i, [_vp, _vp, _l, _l, _i, _f, _vp, _i, _i, _i, C.POINTER(_vp), _vp, C.c_ulonglong, _vp, _vp, _vp, _vp,
+    "efm_bh_dist_fwd_bwd": (_i, [_vp, _vp, _l, _l, _i, _f, _vp, _i, _i, _i, C.POINTER(_vp), C.c_ulonglong, _vp, _vp, _vp, _vp,
                                  _vp, _sz, _vp]),
     "efm_bh_profile_events": (_i, [C.POINTER(_vp), _i]),
     "efm_gallery_scores_f32": (_i, [_vp, _vp, _l, _l, _vp, _l, _vp, _vp]),

@@ -435,7 +435,7 @@ bh_finalize_kernel(const T* __restrict__ E, const float* __restrict__ nrm, int n
   pdl_trigger();
   pdl_wait();                                                        // the mining kernel has completed
   if (df.world > 1 && df.wait_b) {                                   // the peers' original rows (stage B) must have landed
-    if ((int)threadIdx.x < df.world) tc::wait_counter_thread(df.wait_b + threadIdx.x, df.target_b);
+    if ((int)threadIdx.x < df.world && (int)threadIdx.x != df.rank) tc::wait_counter_thread(df.wait_b + threadIdx.x, df.target_b);
     __syncthreads();
   }
   const long li = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -1056,36 +1056,35 @@ extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long 
 //
 // One process per GPU.  Every rank owns an EXCHANGE REGION (efm_xchg_alloc: plain cudaMalloc memory, because CUDA IPC
 // cannot export sub-allocations of a caching allocator) that all peers map through CUDA IPC.  Layout (the same on
-// every rank):  [cnt_a u64[8] | cnt_b u64[8] | cnt_c u64[8] | pad to 256 B | buffer 0 | buffer 1], each buffer =
-//   xm (B_all, Dp) bf16 mining rows | sq (B_all) | lab (B_all) | nrm (B_all) | E (B_all, D) original rows |
-//   res_ip (B_all) | res_in (B_all) | res_w (B_all)
-// with rank r's rows in block r of every array.  Step s uses buffer s & 1; the counters only ever grow (step s waits for
-// s * increments-per-step), so nothing is reset between steps.  A peer can be at most one step ahead (its next Gram
-// kernel needs this rank's next push), hence two buffers suffice.
+// every rank):  [cnt_a u64[8] | cnt_b u64[8] | done, gate, .. | ready u64[8] | buffer 0 | buffer 1], each buffer =
+//   xm (B_all, Dp) bf16 mining rows | sq (B_all) | lab (B_all) | nrm (B_all) | E (B_all, D) original rows (absent when
+//   the rows are bf16 with D % 64 == 0: they are their own mining rows) | res_ip (B_all) | res_in (B_all) | res_w (B_all)
+// with rank r's rows in block r of every array.  Step s uses buffer s & 1; counters and flags only ever grow (step s waits
+// for s * increments-per-step), so nothing is reset between steps.  A peer can be at most one step ahead (its next Gram
+// kernel needs this rank's next block), hence two buffers suffice.
 //
 //   memset        label table + chain heads (local workspace)
 //   bh_prep       LOCAL rows only -> block `rank` of xm / sq / lab / nrm in the own region
-//   gram_kernel   <MineEpi, COMM>: a 19th warp per CTA pushes block `rank` of xm/sq/lab/nrm (stage A) and the original rows
-//                 (stage B) into every peer's region with plain stores over NVLink + one release-add per (CTA, peer,
-//                 stage) on the peer's arrival counter; the tile schedule is column-block-major starting with the
-//                 local block, and the producer / epilogue warps wait for a peer's stage-A counter right before its
-//                 first tile -> the transfer is hidden behind the tiles of the blocks that are already there
-//                 afterwards the same warps register their share of the global batch in the per-label member table
-//   bh_finalize   local anchors (waits for stage B); leaves (idx_p, idx_n, weight) of its anchors in the own region and adds
-//                 one arrival per block to every peer's result counter
-//   bh_chain      exact mode: waits for the peers' result counters, FETCHES their anchors' results over NVLink (12 B per
-//                 anchor instead of a dense reduce-scatter of dE) and chains every anchor that mined a local row
+//   gram_kernel   <MineEpi, COMM>: announces the block to the peers (one flag store each); two extra warps per CTA COPY the
+//                 peers' blocks into the own region with loads over NVLink, in the order of the column-block-major tile
+//                 schedule (local block first), and bump a local arrival counter per block; the producer / epilogue warps
+//                 wait for a block's counter right before its first tile -> the transfer is hidden behind the tiles of the
+//                 blocks that are already there; afterwards the same warps build the per-label member table
+//   bh_finalize   local anchors; leaves (idx_p, idx_n, weight) in the own region, counts finished blocks in a local counter
+//   bh_chain      exact mode: one block waits for the peers' completion counters (read over NVLink), then every thread FETCHES
+//                 one anchor's result from its owner (12 B per anchor instead of a dense reduce-scatter of dE) and chains it
+//                 if it mined a local row
 //   bh_grad       local rows only -> dE_local (B_local, D)
-// No NCCL call and no host synchronisation inside the step.
+// No NCCL call, no host synchronisation, no system-scope fence inside the step.
 namespace efm {
 namespace {
 
-struct XchgLayout { int Dp; bool e_is_xm; size_t cnt_a, cnt_b, cnt_c, buf0, buf_bytes, xm, sq, lab, nrm, E, rip, rin, rw, total; };
+struct XchgLayout { int Dp; bool e_is_xm; size_t cnt_a, cnt_b, cnt_c, ready, buf0, buf_bytes, xm, sq, lab, nrm, E, rip, rin, rw, total; };
 XchgLayout xchg_layout(long B, int world, long D, int dtype) {
   XchgLayout L{};
   L.Dp = (int)(cdiv(D, tc::BK) * tc::BK);
   const size_t B_all = (size_t)B * world;
-  L.cnt_a = 0; L.cnt_b = 64; L.cnt_c = 128; L.buf0 = 256;              // cnt_c: [0] finalize-completion counter, [1] chain gate
+  L.cnt_a = 0; L.cnt_b = 64; L.cnt_c = 128; L.ready = 192; L.buf0 = 256;   // cnt_c: [0] finalize-completion counter, [1] chain gate
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.xm = take(B_all * L.Dp * 2);
@@ -1181,12 +1180,11 @@ extern "C" int efm_ipc_release(void* mapped) {
 
 extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_local, long B_local, long D, int dtype,
                                    float margin, const float* head_grad, int flags, int world, int rank,
-                                   void* const* regions, void* mc_region, unsigned long long step, float* loss, int32_t* idx_p,
+                                   void* const* regions, unsigned long long step, float* loss, int32_t* idx_p,
                                    int32_t* idx_n, float* dE_local, void* workspace, size_t ws_bytes, void* stream) {
   { const int rc = dist_check_shape("efm_bh_dist_fwd_bwd", B_local, world, rank, D, dtype); if (rc) return rc; }
   EFM_REQUIRE(E_local && labels_local && regions && loss && idx_p && idx_n && workspace, EFM_E_ARG, "efm_bh_dist_fwd_bwd: null pointer");
   EFM_REQUIRE(step >= 1, EFM_E_ARG, "efm_bh_dist_fwd_bwd: step counts from 1 (the same value on every rank)");
-  EFM_REQUIRE(!mc_region || aligned(mc_region, 256), EFM_E_ALIGN, "efm_bh_dist_fwd_bwd: multicast region must be 256-byte aligned");
   EFM_REQUIRE(aligned(workspace, 256) && aligned(E_local, 16) && (!dE_local || aligned(dE_local, 16)), EFM_E_ALIGN,
               "efm_bh_dist_fwd_bwd: workspace must be 256-byte, E_local / dE_local 16-byte aligned");
   for (int r = 0; r < world; ++r) EFM_REQUIRE(regions[r] && aligned(regions[r], 256), EFM_E_ARG, "efm_bh_dist_fwd_bwd: region %d missing", r);
@@ -1227,6 +1225,8 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
 
   EFM_BH_STAGE(0, st);
   EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));
+  if (!X.e_is_xm)                                                        // original rows next to the bf16 mining rows (stage B source)
+    EFM_CUDA(cudaMemcpyAsync(buf + X.E + (size_t)row0 * D * es, E_local, (size_t)B * D * es, cudaMemcpyDeviceToDevice, st));
   // 1. local rows -> block `rank` of this step's buffer
   EFM_DISPATCH_DTYPE(dtype, T, {
     bh_prep_kernel<T, true><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_local, labels_local, B, (int)D, X.Dp, normalize, 1, 0, 0, B,
@@ -1243,21 +1243,18 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
     g.phases = world; g.phase0 = rank;
     const int grid = tc::plan_gram(g, 1, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, 2);
     EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "efm_bh_dist_fwd_bwd: D = %ld leaves no shared memory for the B pipeline", D);
-    // arrivals per (sender, stage, step): unicast -- one per CTA (the exchange warp that serves the destination);
-    // multicast -- one per exchange warp (they share every segment)
-    target_ab = step * (unsigned long long)grid * ((mc_region && world > 1) ? tc::COMM_WARPS : 1);
+    target_ab = step * (unsigned long long)grid * tc::COMM_WARPS;        // every exchange warp adds 1 per (block, stage) per step
     g.ready = reinterpret_cast<const unsigned long long*>(own + X.cnt_a);
     g.ready_target = target_ab;
     tc::CommParams cp{};
-    cp.world = world; cp.rank = rank; cp.nseg_a = 4; cp.nseg = X.e_is_xm ? 4 : 5; cp.self_b = X.e_is_xm ? 0 : 1;
+    cp.world = world; cp.rank = rank; cp.nseg_a = 4; cp.nseg = X.e_is_xm ? 4 : 5; cp.step = step;
     for (int r = 0; r < world; ++r) cp.peer[r] = static_cast<uint8_t*>(regions[r]);
-    cp.mc = world > 1 ? static_cast<uint8_t*>(mc_region) : nullptr;
-    cp.seg[0] = {reinterpret_cast<const uint8_t*>(xm + row0 * X.Dp), boff + X.xm + (size_t)row0 * X.Dp * 2, (unsigned long long)B * X.Dp * 2};
-    cp.seg[1] = {reinterpret_cast<const uint8_t*>(sq + row0), boff + X.sq + (size_t)row0 * 4, (unsigned long long)B * 4};
-    cp.seg[2] = {reinterpret_cast<const uint8_t*>(lab + row0), boff + X.lab + (size_t)row0 * 4, (unsigned long long)B * 4};
-    cp.seg[3] = {reinterpret_cast<const uint8_t*>(nrm + row0), boff + X.nrm + (size_t)row0 * 4, (unsigned long long)B * 4};
-    cp.seg[4] = {static_cast<const uint8_t*>(E_local), boff + X.E + (size_t)row0 * D * es, (unsigned long long)B * D * es};
-    cp.cnt_a_off = X.cnt_a; cp.cnt_b_off = X.cnt_b;
+    cp.seg[0] = {boff + X.xm, (unsigned long long)B * X.Dp * 2};
+    cp.seg[1] = {boff + X.sq, (unsigned long long)B * 4};
+    cp.seg[2] = {boff + X.lab, (unsigned long long)B * 4};
+    cp.seg[3] = {boff + X.nrm, (unsigned long long)B * 4};
+    cp.seg[4] = {boff + X.E, (unsigned long long)B * D * es};
+    cp.ready_off = X.ready; cp.cnt_a_off = X.cnt_a; cp.cnt_b_off = X.cnt_b;
     cp.tab_lab = lab; cp.tab_rows = B_all;                               // label table of the global batch, built by the same warps
     cp.hkeys = hkeys; cp.hcnt = hcnt; cp.hmem = hmem; cp.hhead = hhead; cp.hnext = hnext; cp.hslot = hslot; cp.tbits = L.tbits;
     MineEpi::Params ep{sq, lab, kneg, (int)row0, normalize};

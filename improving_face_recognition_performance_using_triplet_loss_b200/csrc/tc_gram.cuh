@@ -57,38 +57,37 @@ struct GramParams {
   int splits;
   // Column blocks ("phases", multi-GPU mining): the N columns are `phases` equal blocks, one per rank, visited
   // block-major starting at block `phase0` (the local rank's rows, already resident).  Before the first tile of any
-  // other block the kernel waits until that block's arrival counter (incremented by the owning peer's pushes over
-  // NVLink, see CommParams) has reached `ready_target`.  phases = 1: one block, no waits.
+  // other block the kernel waits until that block's arrival counter (incremented by this kernel's own exchange warps as
+  // their copies over NVLink complete, see CommParams) has reached `ready_target`.  phases = 1: one block, no waits.
   int phases, phase0;
   const unsigned long long* ready;       // [phases] arrival counters in LOCAL memory; nullptr = nothing to wait for
   unsigned long long ready_target;
 };
 
 // ---- peer exchange fused into the Gram kernel (one process per GPU, peers mapped through CUDA IPC) -------------
-// Every rank owns an exchange region with the same layout.  A rank's kernel PUSHES its own rows into the same offsets
-// of every peer's region with plain stores over NVLink (posted writes; nobody ever reads remote memory), stage A (what
-// the peers' mining needs: bf16 mining rows, |x|^2, labels, norms) before stage B (the original rows, needed only after
-// mining), destinations ordered by when the receiver's block-major schedule reaches this rank's block.  After the share
-// of one CTA for one destination: fence.sys, then one release-add on the destination's arrival counter for this rank.
+// Every rank owns an exchange region with the same layout; rank r's rows live in block r of every array.  The exchange is
+// a PULL: a rank's prep kernel leaves its block in its OWN region, the Gram kernel announces it to the peers with one flag
+// store per peer (the data was written by a previous kernel, so no fence is needed) and the exchange warps of every other
+// rank copy the block into their own region with loads over NVLink -- block by block in the order of the receiver's
+// block-major tile schedule, each warp taking its share of every block.  After a block: a DEVICE-scope fence and one
+// add on the local arrival counter the TMA producer / epilogue warps wait on.  No store ever crosses NVLink except the
+// flags, and no system-scope fence is executed on an SM that runs the tensor pipeline (measured: every MEMBAR.SYS of a
+// push-style exchange costs 10-60 us while the links are busy and stalls the SM's TMA traffic for that long).
 constexpr int MAX_PEERS = 8;
-constexpr int MAX_PUSH_SEGS = 6;
-constexpr int COMM_WARPS = 2;            // exchange warps per CTA (COMM kernels); they alternate over the destinations, so one
-                                         // keeps the link busy while the other sits in the system-scope fence before its signal
-constexpr int PUSH_DEPTH = 8;            // 16-byte loads in flight per lane
-struct PushSeg { const uint8_t* src; unsigned long long dst_off; unsigned long long bytes; };   // 16-byte multiples
+constexpr int MAX_XCHG_SEGS = 6;
+constexpr int COMM_WARPS = 2;            // exchange warps per CTA (COMM kernels): 2 x 32 lanes x 8 x 16 B = 8 KB of loads in flight per SM
+constexpr int PULL_DEPTH = 8;            // 16-byte loads in flight per lane
+struct XchgSeg { unsigned long long off; unsigned long long bytes; };   // offset of block 0 of an array inside a region; bytes per rank block
 struct CommParams {
   int world, rank;
-  int nseg_a, nseg;                      // segments [0, nseg_a): stage A, [nseg_a, nseg): stage B
-  int self_b;                            // stage B is also copied into this rank's OWN region (last), so that the
-                                         // gathered rows are contiguous locally without a separate copy
+  int nseg_a, nseg;                      // segments [0, nseg_a): stage A (what mining needs), [nseg_a, nseg): stage B (only read after mining)
   uint8_t* peer[MAX_PEERS];              // base of rank r's exchange region as mapped in this process (peer[rank] = own)
-  uint8_t* mc;                           // NVLS multicast alias of ALL regions (nullptr: unicast pushes, one per peer).  One
-                                         // multimem.st is replicated by the NVSwitch into every rank's region (own included), so
-                                         // a rank sends its rows ONCE instead of world - 1 times
-  PushSeg seg[MAX_PUSH_SEGS];
-  unsigned long long cnt_a_off, cnt_b_off;   // offsets of the u64[world] arrival counters inside a region
-  // Second job of the exchange warp, after its pushes: once stage A of every rank has arrived (the labels of the whole
-  // global batch are local), register this CTA's share of the rows in the per-label member table that the finalize
+  XchgSeg seg[MAX_XCHG_SEGS];
+  unsigned long long ready_off;          // u64[world] in every region: ready[r] = last step whose block rank r has announced
+  unsigned long long cnt_a_off, cnt_b_off;   // u64[world] LOCAL arrival counters per source rank, stage A / stage B
+  unsigned long long step;
+  // Second job of the exchange warps, after their copies: once stage A of every rank has arrived (the labels of the whole
+  // global batch are local), register this warp's share of the rows in the per-label member table that the finalize
   // kernel reads -- the table build is hidden behind the Gram tiles instead of being a kernel of its own.
   const int32_t* tab_lab;                // (tab_rows) labels, nullptr = no table job
   long tab_rows;
@@ -253,87 +252,49 @@ __device__ __forceinline__ void wait_counter(const unsigned long long* p, unsign
   if ((threadIdx.x & 31) == 0) wait_counter_thread(p, target);
   __syncwarp();
 }
-// one warp copies its share of a segment: 16-byte units, PUSH_DEPTH loads in flight per lane, plain (posted) stores
-__device__ __forceinline__ void push_share(uint8_t* dst, const uint8_t* src, unsigned long long bytes, int part, int nparts, int lane) {
+// one warp copies its share of a block of a segment: 16-byte units, PULL_DEPTH loads (over NVLink) in flight per lane
+__device__ __forceinline__ void pull_share(uint8_t* dst, const uint8_t* src, unsigned long long bytes, int part, int nparts, int lane) {
   const long U = (long)(bytes >> 4);
   const long lo = U * part / nparts, hi = U * (part + 1) / nparts;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
   long u = lo + lane;
-  for (; u + (PUSH_DEPTH - 1) * 32 < hi; u += PUSH_DEPTH * 32) {
-    uint4 v[PUSH_DEPTH];
+  for (; u + (PULL_DEPTH - 1) * 32 < hi; u += PULL_DEPTH * 32) {
+    uint4 v[PULL_DEPTH];
 #pragma unroll
-    for (int k = 0; k < PUSH_DEPTH; ++k) v[k] = __ldcg(s4 + u + k * 32);
+    for (int k = 0; k < PULL_DEPTH; ++k) v[k] = __ldcg(s4 + u + k * 32);
 #pragma unroll
-    for (int k = 0; k < PUSH_DEPTH; ++k) d4[u + k * 32] = v[k];
+    for (int k = 0; k < PULL_DEPTH; ++k) d4[u + k * 32] = v[k];
   }
   for (; u < hi; u += 32) d4[u] = __ldcg(s4 + u);
 }
-// ---- NVLS multicast (multimem) ------------------------------------------------------------------------------
-__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
-  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
-               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void multimem_red_release_add_u64(void* mc_addr, unsigned long long v) {
-  asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(mc_addr), "l"(v) : "memory");
-}
-// writes through the multicast alias are read through the unicast address: order the two aliases (reader side)
-__device__ __forceinline__ void fence_proxy_alias() { asm volatile("fence.proxy.alias;" ::: "memory"); }
-
-__device__ __forceinline__ void push_share_mc(uint8_t* mc_dst, const uint8_t* src, unsigned long long bytes, int part, int nparts, int lane) {
-  const long U = (long)(bytes >> 4);
-  const long lo = U * part / nparts, hi = U * (part + 1) / nparts;
-  const uint4* s4 = reinterpret_cast<const uint4*>(src);
-  uint4* d4 = reinterpret_cast<uint4*>(mc_dst);
-  long u = lo + lane;
-  for (; u + (PUSH_DEPTH - 1) * 32 < hi; u += PUSH_DEPTH * 32) {
-    uint4 v[PUSH_DEPTH];
-#pragma unroll
-    for (int k = 0; k < PUSH_DEPTH; ++k) v[k] = __ldcg(s4 + u + k * 32);
-#pragma unroll
-    for (int k = 0; k < PUSH_DEPTH; ++k) multimem_st_v4(d4 + u + k * 32, v[k]);
-  }
-  for (; u < hi; u += 32) multimem_st_v4(d4 + u, __ldcg(s4 + u));
-}
-// Multicast push of exchange warp `part` of `nparts` (all exchange warps of the grid share every segment): one pass per
-// stage, one fence, one multicast release-add that bumps this rank's arrival counter in EVERY region.
-__device__ __forceinline__ void comm_push_mc(const CommParams& cp, int part, int nparts, unsigned long long* trace) {
+// The exchange of one warp (`part` of `nparts` over the whole grid): for every peer block in schedule order, wait for the
+// owner's announcement, copy this warp's share of every segment of the stage, publish it locally.
+__device__ __forceinline__ void comm_pull(const CommParams& cp, int part, int nparts, unsigned long long* trace) {
   const int lane = threadIdx.x & 31;
+  uint8_t* own = cp.peer[cp.rank];
+  const unsigned long long* ready = reinterpret_cast<const unsigned long long*>(own + cp.ready_off);
   for (int stage = 0; stage < 2; ++stage) {
-    if (stage && trace && lane == 0) trace[9] = gtimer();
+    if (stage && trace && lane == 0) trace[9] = gtimer();            // stage A complete (this warp's shares)
     const int s0 = stage ? cp.nseg_a : 0, s1 = stage ? cp.nseg : cp.nseg_a;
     if (s0 == s1) continue;
-    for (int s = s0; s < s1; ++s) push_share_mc(cp.mc + cp.seg[s].dst_off, cp.seg[s].src, cp.seg[s].bytes, part, nparts, lane);
-    const unsigned long long tf = trace ? gtimer() : 0ull;
-    fence_acq_rel_sys();
-    __syncwarp();
-    if (lane == 0) {
-      multimem_red_release_add_u64(cp.mc + (stage ? cp.cnt_b_off : cp.cnt_a_off) + 8ull * cp.rank, 1ull);
-      if (trace) trace[15] += gtimer() - tf;
-    }
-  }
-}
-
-// The push of one CTA (`part` of `nparts`): exchange warp `cw` serves every COMM_WARPS-th destination.
-__device__ __forceinline__ void comm_push(const CommParams& cp, int part, int nparts, int cw, unsigned long long* trace) {
-  const int lane = threadIdx.x & 31;
-  for (int stage = 0; stage < 2; ++stage) {
-    if (stage && trace && lane == 0) trace[9] = gtimer();            // this warp's stage A pushed
-    const int s0 = stage ? cp.nseg_a : 0, s1 = stage ? cp.nseg : cp.nseg_a;
-    if (s0 == s1) continue;
-    const int last = (stage && cp.self_b) ? cp.world : cp.world - 1; // ph = world: this rank's own region
-    for (int ph = 1; ph <= last; ++ph) {
-      if ((ph % COMM_WARPS) != cw) continue;
-      int dest = cp.rank - ph; if (dest < 0) dest += cp.world;       // the receiver that reaches this rank's block at phase ph
-      uint8_t* base = cp.peer[dest];
-      for (int s = s0; s < s1; ++s) push_share(base + cp.seg[s].dst_off, cp.seg[s].src, cp.seg[s].bytes, part, nparts, lane);
-      const unsigned long long tf = trace ? gtimer() : 0ull;
-      fence_acq_rel_sys();                                           // the whole warp: its stores have been performed at the peer
-      __syncwarp();
-      if (lane == 0) {
-        red_relaxed_sys_add_u64(reinterpret_cast<unsigned long long*>(base + (stage ? cp.cnt_b_off : cp.cnt_a_off)) + cp.rank, 1ull);
-        if (trace) trace[15] += gtimer() - tf;                       // time spent in fences
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(own + (stage ? cp.cnt_b_off : cp.cnt_a_off));
+    for (int ph = 1; ph < cp.world; ++ph) {
+      int blk = cp.rank + ph; if (blk >= cp.world) blk -= cp.world;  // the block this rank's tile schedule reaches at phase ph
+      const unsigned long long tw = trace ? gtimer() : 0ull;
+      wait_counter(ready + blk, cp.step);                            // the owner's prep of this step has completed
+      if (trace && lane == 0) trace[15] += gtimer() - tw;
+      const uint8_t* src = cp.peer[blk];
+      for (int s = s0; s < s1; ++s) {
+        const unsigned long long o = cp.seg[s].off + (unsigned long long)blk * cp.seg[s].bytes;
+        pull_share(own + o, src + o, cp.seg[s].bytes, part, nparts, lane);
       }
+      __threadfence();                                               // device scope: the copies are in L2
+      __syncwarp();
+      if (lane == 0) atomicAdd(cnt + blk, 1ull);
     }
   }
 }
@@ -509,7 +470,7 @@ template <int MH> inline int pick_stages(int nk, int extra) {
 // which reads both halves, so every SM pulls half the B bytes from L2 and reads half the B bytes from shared memory per
 // MAC.  Barriers: full / a_full / acc_empty live in the leader (TMA of both CTAs credits the leader, the peer's epilogue
 // arrives remotely); empty / a_empty / acc_full are signalled in both CTAs by multicast tcgen05.commit.
-// COMM: COMM_WARPS extra warps push this rank's rows to the peers' exchange regions while the tiles run (see CommParams).
+// COMM: COMM_WARPS extra warps copy the peers' rows into this rank's exchange region while the tiles run (see CommParams).
 template <class Epi, int MH, int CG, bool COMM>
 __global__ void __launch_bounds__(THREADS + (COMM ? 32 * COMM_WARPS : 0), 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams g,
@@ -574,8 +535,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (it.new_phase && it.ph > 0 && g.ready) {                    // a peer's column block: wait until it has landed
         const unsigned long long tw = g.trace ? gtimer() : 0ull;
         wait_counter(g.ready + it.block(), g.ready_target);
-        fence_proxy_alias();                                         // the rows may have been written through the multicast alias
-        fence_proxy_async_all();                                     // remote generic-proxy writes -> our TMA (async proxy) reads
+        fence_proxy_async_all();                                     // the exchange warps' generic-proxy writes -> our TMA (async proxy) reads
         if (g.trace && lane == 0) {
           g.trace[(size_t)blockIdx.x * TRACE_SLOTS + 13] += gtimer() - tw;
           g.trace[(size_t)blockIdx.x * TRACE_SLOTS + 14] += 1;
@@ -676,7 +636,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     TileIter<CG> nx(g);
     bool has = nx.next();
     if (has) {
-      if (nx.ph > 0 && g.ready) { wait_counter(g.ready + nx.block(), g.ready_target); fence_proxy_alias(); }   // no tile in the local block
+      if (nx.ph > 0 && g.ready) wait_counter(g.ready + nx.block(), g.ready_target);   // no tile in the local block
       Epi::prefetch(ep, g, scratch, 0, nx.ct() * BN + cs * COLS_PER_WARP);
     }
     int i = 0;
@@ -690,7 +650,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       has = nx.next();                                               // nx now describes the tile after this one
       Epi::prefetch_wait();                                          // this tile's per-column data has landed
       if (has) {                                                     // next tile's data: in flight during this tile
-        if (nx.new_phase && g.ready) { wait_counter(g.ready + nx.block(), g.ready_target); fence_proxy_alias(); }   // ... once its block has arrived
+        if (nx.new_phase && g.ready) wait_counter(g.ready + nx.block(), g.ready_target);   // ... once its block has arrived
         Epi::prefetch(ep, g, scratch, (i + 1) & 1, nx.ct() * BN + cs * COLS_PER_WARP);
       }
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
@@ -723,17 +683,21 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (COMM && warp > MMA_WARP) {
     const int cw = warp - (MMA_WARP + 1);
     const int part = (int)blockIdx.x * COMM_WARPS + cw, nparts = (int)gridDim.x * COMM_WARPS;
-    const bool tr = g.trace && cw == 1;                              // warp 1 serves the first destination
+    const bool tr = g.trace && cw == 0;
     if (tr) EFM_TRACE(8);
-    if (cp.mc) comm_push_mc(cp, part, nparts, tr ? g.trace + (size_t)blockIdx.x * TRACE_SLOTS : nullptr);
-    else if (cp.world > 1 || cp.self_b)
-      comm_push(cp, (int)blockIdx.x, (int)gridDim.x, cw, tr ? g.trace + (size_t)blockIdx.x * TRACE_SLOTS : nullptr);
+    if (cp.world > 1) {
+      if (blockIdx.x == 0 && cw == 0) {                               // announce this rank's block: one flag store per peer
+        fence_acq_rel_sys();                                           // (one warp of one CTA, nothing in flight yet: cheap)
+        if (lane < cp.world && lane != cp.rank)
+          st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(cp.peer[lane] + cp.ready_off) + cp.rank, cp.step);
+      }
+      comm_pull(cp, part, nparts, tr ? g.trace + (size_t)blockIdx.x * TRACE_SLOTS : nullptr);
+    }
     if (tr) EFM_TRACE(10);
     if (cp.tab_lab) {
       if (g.ready)
         for (int r = 0; r < cp.world; ++r)
           if (r != cp.rank) wait_counter(g.ready + r, g.ready_target);       // labels of every rank are here
-      fence_proxy_alias();
       if (tr) EFM_TRACE(11);
       const long lo = cp.tab_rows * part / nparts, hi = cp.tab_rows * (part + 1) / nparts;
       for (long row = lo + lane; row < hi; row += 32)

@@ -70,14 +70,13 @@ class PeerExchange:
 
     Every rank allocates a region through libefmtl (`efm_xchg_alloc`), the 64-byte CUDA IPC handles travel through
     `torch.distributed` (any backend: they are host bytes), and every rank maps every peer's region.  After that
-    `step()` needs no collective at all: the Gram + mining kernel pushes this rank's rows to the peers over NVLink
-    while it runs (csrc/bh.cu, efm_bh_dist_fwd_bwd).  All ranks must call `step()` the same number of times with
-    the same shapes and flags."""
+    `step()` needs no collective at all: the Gram + mining kernel copies the peers' rows over NVLink while it runs
+    (csrc/bh.cu, efm_bh_dist_fwd_bwd).  All ranks must call `step()` the same number of times with the same shapes
+    and flags."""
 
-    def __init__(self, B_local: int, D: int, dtype: torch.dtype, device=None, group=None, multicast=None):
-        """multicast: None = use NVLS multicast when torch's symmetric memory offers it, True = require it, False = CUDA IPC
-        regions with one unicast push per peer."""
+    def __init__(self, B_local: int, D: int, dtype: torch.dtype, device=None, group=None):
         import ctypes as C
+        import socket
 
         from . import _lib as L
         self._L, self._C = L, C
@@ -92,62 +91,18 @@ class PeerExchange:
             raise ValueError("fused exchange needs B_local % 256 == 0, D % 8 == 0, D <= 512, world <= 8 "
                              "(got B_local=%d D=%d world=%d)" % (self.B, self.D, self.world))
         self.nbytes = nbytes
-        self._own = None
-        self._mapped = []
-        self._symm = None
-        self.mc = None
-        self.regions = (C.c_void_p * self.world)()
-        if self.world > 1 and multicast is not False:
-            self._try_symmetric_memory(require=bool(multicast))
-        if self._symm is None:
-            self._ipc_regions()
-        self.mode = "nvls-multicast" if self.mc else ("ipc-unicast" if self.world > 1 else "single")
-        self.ws = L.workspace(L.lib.efm_bh_dist_workspace_bytes(self.B, self.world), self.device)
-        self.steps = 0
-        if self.world > 1:
-            dist.barrier(group=self.group)     # nobody pushes before every region exists, is zeroed and is mapped
-
-    def _try_symmetric_memory(self, require):
-        """Regions from torch.distributed._symmetric_memory (plumbing: allocation, handle exchange, NVLS multicast binding).
-        All ranks decide together; any failure falls back to the IPC regions unless multicast was required."""
-        t = h = None
-        err = ""
-        try:
-            import torch.distributed._symmetric_memory as symm
-            t = symm.empty(self.nbytes, dtype=torch.uint8, device=self.device)
-            pg = self.group if self.group is not None else dist.group.WORLD
-            h = symm.rendezvous(t, pg.group_name)
-            ok = int(getattr(h, "multicast_ptr", 0) or 0) != 0 and len(h.buffer_ptrs) == self.world
-            if not ok:
-                err = "no multicast pointer"
-        except Exception as e:  # noqa: BLE001
-            ok, err = False, repr(e)
-        flag = torch.tensor([1 if ok else 0], device=self.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        if not int(flag):
-            if require:
-                raise RuntimeError("PeerExchange: NVLS multicast regions unavailable (%s)" % (err or "a peer failed"))
-            return
-        t.zero_()                              # arrival counters start at 0
-        torch.cuda.synchronize(self.device)
-        self._symm = (t, h)
-        for r in range(self.world):
-            self.regions[r] = int(h.buffer_ptrs[r])
-        self.mc = self._C.c_void_p(int(h.multicast_ptr))
-
-    def _ipc_regions(self):
-        import socket
-        C, L = self._C, self._L
         self._own = C.c_void_p()
+        self._mapped = []
+        self.regions = (C.c_void_p * self.world)()
         with torch.cuda.device(self.device):
-            L.check(L.lib.efm_xchg_alloc(self.nbytes, C.byref(self._own)))
+            L.check(L.lib.efm_xchg_alloc(nbytes, C.byref(self._own)))
             handle = C.create_string_buffer(64)
             L.check(L.lib.efm_ipc_export(self._own, handle))
             mine = (socket.gethostname(), handle.raw)
             everyone = [mine]
             if self.world > 1:
                 everyone = [None] * self.world
-                dist.all_gather_object(everyone, mine, group=self.group)
+                dist.all_gather_object(everyone, mine, group=group)
                 if any(h != mine[0] for h, _ in everyone):
                     raise RuntimeError("PeerExchange: all ranks must run on one node (CUDA IPC over NVLink)")
             for r, (_, raw) in enumerate(everyone):
@@ -158,6 +113,11 @@ class PeerExchange:
                     L.check(L.lib.efm_ipc_import(raw, C.byref(p)))
                     self._mapped.append(p)
                     self.regions[r] = p.value
+        self.mode = "ipc-pull" if self.world > 1 else "single"
+        self.ws = L.workspace(L.lib.efm_bh_dist_workspace_bytes(self.B, self.world), self.device)
+        self.steps = 0
+        if self.world > 1:
+            dist.barrier(group=group)          # nobody reads a region before it exists, is zeroed and is mapped everywhere
 
     def step(self, E_local, labels_local, margin, *, normalize=True, exact_grad=True, want_grad=True, head_grad=None,
              out=None):
@@ -185,25 +145,24 @@ class PeerExchange:
         self.steps += 1
         with torch.cuda.device(dev):
             L.check(L.lib.efm_bh_dist_fwd_bwd(L.ptr(E_local), L.ptr(lab), self.B, self.D, self.dt, float(margin), L.ptr(hg),
-                                              flags, self.world, self.rank, self.regions, self.mc, self.steps, L.ptr(loss),
+                                              flags, self.world, self.rank, self.regions, self.steps, L.ptr(loss),
                                               L.ptr(idx_p), L.ptr(idx_n), L.ptr(dE), L.ptr(self.ws), self.ws.numel(),
                                               L.stream()))
         return loss, idx_p, idx_n, dE
 
     def close(self):
-        """Collective: every rank must call it (peers may still be writing into this rank's region otherwise)."""
-        if self._own is None and self._symm is None:
+        """Collective: every rank must call it (peers may still be reading this rank's region otherwise)."""
+        if self._own is None:
             return
         torch.cuda.synchronize(self.device)
         if self.world > 1 and dist.is_initialized():
             dist.barrier(group=self.group)
         L = self._L
-        if self._own is not None:
-            with torch.cuda.device(self.device):
-                for p in self._mapped:
-                    L.lib.efm_ipc_release(p)
-                L.lib.efm_xchg_free(self._own)
-        self._mapped, self._own, self._symm, self.mc = [], None, None, None
+        with torch.cuda.device(self.device):
+            for p in self._mapped:
+                L.lib.efm_ipc_release(p)
+            L.lib.efm_xchg_free(self._own)
+        self._mapped, self._own = [], None
 
 
 def global_batch_hard_fused(exchange: PeerExchange, E_local, labels_local, margin, *, normalize=True, exact_grad=True,

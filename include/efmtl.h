@@ -152,16 +152,10 @@ int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype, int flags
  * step and must call efm_bh_dist_fwd_bwd with the same shapes, flags and `step` (1, 2, 3, ... -- it selects one of two
  * buffers and the value the arrival counters are compared with; nothing is reset between steps).
  *
- * `mc_region` (optional, NULL = none): an NVLS MULTICAST alias of the same regions (all ranks' regions bound to one
- * multicast object at the same offsets, e.g. torch.distributed._symmetric_memory's `multicast_ptr`; the regions then
- * come from that allocator instead of efm_xchg_alloc and must be zero-filled once).  With it a rank stores its rows
- * ONCE (multimem.st, replicated by the NVSwitch into every region) instead of once per peer.  All ranks must agree on
- * whether they pass it.
- *
- * The step enqueues prep (local rows) -> Gram + mining kernel that also PUSHES this rank's rows into every peer's
- * region over NVLink, waits, column block by column block, for the peers' rows and builds the label table of the
- * global batch (see csrc/bh.cu) -> finalize -> (exact mode) chain kernel that fetches 12 bytes per anchor from the
- * owners over NVLink -> gradient of the local rows.  No NCCL call, no
+ * The step enqueues prep (local rows) -> Gram + mining kernel whose extra warps COPY the peers' rows into the own
+ * region with loads over NVLink (block by block, in the order the tile schedule needs them) and build the label table
+ * of the global batch (see csrc/bh.cu) -> finalize -> (exact mode) chain kernel that fetches 12 bytes per anchor from
+ * the owners over NVLink -> gradient of the local rows.  No NCCL call, no
  * host synchronisation.  Results equal efm_bh_triplet_fwd_bwd on the concatenated batch: loss / idx_p / idx_n
  * (B_local; indices are global rows), dE_local (B_local, D) fp32 or NULL (forward only).  EFM_BH_DETACH_GATHERED:
  * gradient only through roles played by local rows of local anchors (no result exchange).  Mining always runs on the
@@ -176,7 +170,7 @@ int efm_ipc_import(const void* handle64, void** mapped);
 int efm_ipc_release(void* mapped);
 int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_local, long B_local, long D, int dtype,
                         float margin, const float* head_grad, int flags, int world, int rank,
-                        void* const* regions, void* mc_region, unsigned long long step, float* loss, int32_t* idx_p,
+                        void* const* regions, unsigned long long step, float* loss, int32_t* idx_p,
                         int32_t* idx_n, float* dE_local, void* workspace, size_t ws_bytes, void* stream);
 /* Profiling aid: the following efm_bh_triplet_fwd_bwd / efm_bh_dist_fwd_bwd calls of this thread record
  * events[i] (cudaEvent_t passed as void*, NULL entries skipped) on the call's stream at stage boundary i:

@@ -37,10 +37,8 @@ def main():
 
     B, Dm, G = args.B, args.D, args.B * world
     ok = True
-    for dtype, mc in ((torch.bfloat16, None), (torch.bfloat16, False), (torch.float32, None)):
-        px = D.PeerExchange(B, Dm, dtype, multicast=mc)       # None: NVLS multicast pushes if available; False: unicast over CUDA IPC
-        if rank == 0:
-            print("exchange mode:", px.mode, dtype, flush=True)
+    for dtype in (torch.bfloat16, torch.float32):
+        px = D.PeerExchange(B, Dm, dtype)
         for s in range(args.steps):
             E, y = clustered(G, Dm, seed=100 + s)
             Eg, yg = torch.from_numpy(E).to(dev).to(dtype), torch.from_numpy(y).to(dev)

@@ -17,12 +17,12 @@ from improving_face_recognition_performance_using_triplet_loss_b200 import distr
 G = int(os.environ.get("KB_G", 65536)); B = G // world; Dm = 256
 E, y = bench.make_batch(G, Dm, 0)
 El = torch.from_numpy(E[rank * B:(rank + 1) * B]).to(torch.bfloat16).to(dev); yl = torch.from_numpy(y[rank * B:(rank + 1) * B]).to(dev)
-px = D.PeerExchange(B, Dm, torch.bfloat16, device=dev, multicast={'auto': None, 'on': True, 'off': False}[os.environ.get('KB_MC', 'auto')])
+px = D.PeerExchange(B, Dm, torch.bfloat16, device=dev)
 for _ in range(3):
     px.step(El, yl, 0.2)
 torch.cuda.synchronize(); dist.barrier()
-names = {1: "prologue done", 3: "first acc_full", 6: "last tile epilogue done", 7: "exit", 8: "push start", 9: "stage A pushed",
-         10: "stage B pushed", 11: "all labels here", 12: "label table done"}
+names = {1: "prologue done", 3: "first acc_full", 6: "last tile epilogue done", 7: "exit", 8: "exchange start", 9: "stage A copied",
+         10: "stage B copied", 11: "all labels here", 12: "label table done"}
 for it in range(3):
     trace.zero_(); torch.cuda.synchronize(); dist.barrier()
     px.step(El, yl, 0.2)
@@ -35,7 +35,7 @@ for it in range(3):
         for k in sorted(names):
             col = (t[:, k] - t0) / 1e3
             out.append("  %-26s min %8.1f  median %8.1f  max %8.1f us" % (names[k], col.min(), np.median(col), col.max()))
-        out.append("  exchange warp 1: %.1f us median in system fences" % (np.median(t[:, 15]) / 1e3))
+        out.append("  exchange warp 0: %.1f us median waiting for the owners' announcements" % (np.median(t[:, 15]) / 1e3))
         out.append("  producer peer waits: median %.1f us, max %.1f us per CTA over %d waits" % (np.median(t[:, 13]) / 1e3, t[:, 13].max() / 1e3, int(t[:, 14].max())))
         for r in range(world):
             dist.barrier()
