@@ -287,7 +287,8 @@ struct MineEpi {
       }
     }
     const float m = fminf(fminf(fminf(pm[0], pm[1]), pm[2]), pm[3]);
-    if (m < s.nbest) {                               // strict: the earlier group survives ties
+    // ties go to the lower column whatever the visiting order (the multi-GPU schedule is block-major and serpentine)
+    if (m < s.nbest || (m == s.nbest && col0 < s.ngrp)) {
       int q = 3;
       q = (pm[2] == m) ? 2 : q;
       q = (pm[1] == m) ? 1 : q;

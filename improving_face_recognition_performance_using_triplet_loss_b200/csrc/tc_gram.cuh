@@ -75,8 +75,8 @@ struct GramParams {
 // push-style exchange costs 10-60 us while the links are busy and stalls the SM's TMA traffic for that long).
 constexpr int MAX_PEERS = 8;
 constexpr int MAX_XCHG_SEGS = 6;
-constexpr int COMM_WARPS = 2;            // exchange warps per CTA (COMM kernels): 2 x 32 lanes x 8 x 16 B = 8 KB of loads in flight per SM
-constexpr int PULL_DEPTH = 8;            // 16-byte loads in flight per lane
+constexpr int COMM_WARPS = 2;            // exchange warps per CTA (COMM kernels): 2 x 32 lanes x 16 x 16 B = 16 KB of loads in flight per SM
+constexpr int PULL_DEPTH = 16;           // 16-byte loads in flight per lane (the copy is latency-bound: ~8 us per round trip under load)
 struct XchgSeg { unsigned long long off; unsigned long long bytes; };   // offset of block 0 of an array inside a region; bytes per rank block
 struct CommParams {
   int world, rank;
@@ -395,18 +395,20 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 
 // ---- tile schedule -------------------------------------------------------------------------------------
 // Tiles are visited phase by phase (one phase = one column block; a single phase unless the columns come from several
-// ranks).  Inside a phase a CTA (pair) owns a contiguous range of the phase's tiles in row-major order, so its A row
-// block stays resident while it walks column tiles.  All three roles (TMA, MMA, epilogue) run the same iterator.
+// ranks).  Inside a phase a CTA (pair) owns a contiguous range of the phase's tiles in row-major order -- the same range in
+// every phase -- so its A row block stays resident while it walks column tiles.  Odd phases walk the range BACKWARDS
+// (serpentine): a phase starts in the row block the previous one ended in, so a phase boundary costs no A reload, no
+// accumulator drain and no row-state flush.  All three roles (TMA, MMA, epilogue) run the same iterator.
 template <int CG>
 struct TileIter {
   int CTp, phases, phase0;   // column tiles per phase
   int sched_mode, splits, row_blocks;
-  int ph, left;              // current phase; tiles left in it after the current one
+  int ph, left, dir;         // current phase; tiles left in it after the current one; walking direction
   int rb, ctl, ct0;          // row block; column tile inside the phase's block; first column tile of that block
   bool new_rb, new_phase;
   __device__ __forceinline__ explicit TileIter(const GramParams& g)
       : CTp(g.col_tiles / g.phases), phases(g.phases), phase0(g.phase0), sched_mode(g.sched_mode), splits(g.splits),
-        row_blocks(g.row_blocks), ph(-1), left(0), rb(0), ctl(0), ct0(0), new_rb(false), new_phase(false) {}
+        row_blocks(g.row_blocks), ph(-1), left(0), dir(1), rb(-1), ctl(0), ct0(0), new_rb(false), new_phase(false) {}
   __device__ __forceinline__ void range(long& t0, long& t1) const {
     const long CT = CTp;
     if (sched_mode == 0) {
@@ -424,7 +426,8 @@ struct TileIter {
     if (left > 0) {
       --left;
       new_phase = false;
-      if (++ctl == CTp) { ctl = 0; ++rb; new_rb = true; } else new_rb = false;
+      if (dir > 0) { if (++ctl == CTp) { ctl = 0; ++rb; new_rb = true; } else new_rb = false; }
+      else { if (--ctl < 0) { ctl = CTp - 1; --rb; new_rb = true; } else new_rb = false; }
       return true;
     }
     while (++ph < phases) {
@@ -432,10 +435,15 @@ struct TileIter {
       range(t0, t1);                                                 // the only divisions: once per phase
       if (t1 > t0) {
         left = (int)(t1 - t0) - 1;
-        rb = (int)(t0 / CTp); ctl = (int)(t0 % CTp);
+        dir = (ph & 1) ? -1 : 1;
+        const long start = dir > 0 ? t0 : t1 - 1;
+        const int nrb = (int)(start / CTp);
+        ctl = (int)(start % CTp);
         int blk = phase0 + ph; if (blk >= phases) blk -= phases;
         ct0 = blk * CTp;
-        new_rb = new_phase = true;
+        new_rb = nrb != rb;                                          // rb = -1 before the first tile
+        rb = nrb;
+        new_phase = true;
         return true;
       }
     }

@@ -333,8 +333,14 @@ def test_bh_block_major_column_schedule(P, phases, monkeypatch):
     """The multi-GPU tile schedule (column blocks visited block-major, starting at the anchors' own block) mines the same
     triplets as the plain row-major schedule.  EFM_GRAM_PHASES is the single-GPU test hook for it."""
     E, y = clustered(2048, 256, seed=41)
+    for src, dups in ((100, (700, 1900)), (1300, (40, 1999))):       # exact duplicate rows in different column blocks: the mined
+        for d in dups:                                               # negative must be the lowest index whatever the visiting order
+            E[d] = E[src]
     Et, yt = dev(E, torch.bfloat16), dev(y)
     full = P.batch_hard_triplet(Et, yt, 1.9)
+    ref = O.batch_hard_triplet(Et.float().cpu().numpy(), y, 1.9, mine_bf16=True)
+    assert np.array_equal(full[1].cpu().numpy(), ref["idx_p"]) and np.array_equal(full[2].cpu().numpy(), ref["idx_n"])
+    assert set(full[2].cpu().numpy().tolist()) & {40, 100, 700, 1300}    # the duplicated rows do get mined (ties are exercised)
     monkeypatch.setenv("EFM_GRAM_PHASES", str(phases))
     for r in range(2):
         l, ip, inn, _ = P.batch_hard_triplet(Et, yt, 1.9, row_offset=r * 1024, num_local=1024)
