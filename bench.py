@@ -408,7 +408,7 @@ def run_ours(args):
         pk, pk_src = peaks()
         flops = 2.0 * B * G * DIM                                      # full Gram strip, symmetry not credited
         traffic = None                                                 # dram bytes of one launch, from the committed ncu capture
-        tf = os.path.join(ROOT, "profiles", "r1_gram_final_summary.json")
+        tf = os.path.join(ROOT, "profiles", "r1_gram_final2_summary.json")
         if world == 1 and name == "c2" and os.path.exists(tf):
             with open(tf) as f:
                 traffic = json.load(f).get("traffic_bytes_per_launch")

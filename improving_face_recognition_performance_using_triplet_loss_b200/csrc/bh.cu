@@ -94,8 +94,13 @@ bh_prep_kernel(const T* __restrict__ E, const int32_t* __restrict__ labels, long
                float* __restrict__ xm_f32, unsigned long long* __restrict__ kpos,
                unsigned long long* __restrict__ kneg, float* __restrict__ dE,
                unsigned long long* __restrict__ hkeys, int32_t* __restrict__ hcnt, int32_t* __restrict__ hmem,
-               int32_t* __restrict__ hhead, int32_t* __restrict__ hnext, int32_t* __restrict__ hslot, int tbits) {
+               int32_t* __restrict__ hhead, int32_t* __restrict__ hnext, int32_t* __restrict__ hslot, int tbits,
+               uint4* __restrict__ clr, long clr_n16) {
   pdl_trigger();                                    // the Gram kernel's prologue may overlap this kernel's tail
+  // reset of the label table and the gradient chain heads (all-ones bytes), folded into this kernel when nothing in it
+  // touches them (the table is then built inside the Gram kernel): saves a memset node and its launch gap
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < clr_n16; i += (long)gridDim.x * blockDim.x)
+    clr[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   const long row = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= B_all) return;
   const int lane = threadIdx.x & 31;
@@ -721,8 +726,16 @@ static bool bh_mine_in_place(const BhLayout& L, const void* E_all, long D, int d
   return L.use_tc && dtype == EFM_BF16 && D == L.Dp && aligned(E_all, 16);
 }
 
+// true when the step's Gram kernel is the variant with the extra warps (CTA pairs): they build the per-label member table
+// while the tiles run, so bh_prep does not have to
+static bool bh_table_in_gram(const BhLayout& L, long B_local) {
+  if (!L.use_tc) return false;
+  const int mh = tc::pick_mh((int)B_local, L.Dp / tc::BK);
+  return tc::pick_cg((int)B_local, mh, 0) == 2;
+}
+
 static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, long B_all, long row_offset, long B_local,
-                            long D, int dtype, int normalize, cudaStream_t st, bool pdl = false) {
+                            long D, int dtype, int normalize, cudaStream_t st, bool pdl = false, bool build_table = false) {
   auto* kpos = reinterpret_cast<unsigned long long*>(ws + L.kpos);
   auto* kneg = reinterpret_cast<unsigned long long*>(ws + L.kneg);
   float* sq = reinterpret_cast<float*>(ws + L.sq);
@@ -741,6 +754,16 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
     }
     const int grid = tc::plan_gram(g, mh, 0, MineEpi::SMEM_PER_WARP * tc::EPI_WARPS, cg);
     MineEpi::Params ep{sq, lab, kneg, (int)row_offset, normalize};
+    if (build_table && cg == 2) {                                    // single-GPU use of the exchange warps: the label table only
+      EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "gram: K = %d leaves no shared memory for the B pipeline", g.nk * tc::BK);
+      tc::CommParams cp{};
+      cp.world = 1;
+      cp.tab_lab = lab; cp.tab_rows = B_all;
+      cp.hkeys = reinterpret_cast<unsigned long long*>(ws + L.hkeys); cp.hcnt = reinterpret_cast<int32_t*>(ws + L.hcnt);
+      cp.hmem = reinterpret_cast<int32_t*>(ws + L.hmem); cp.hhead = reinterpret_cast<int32_t*>(ws + L.hhead);
+      cp.hnext = reinterpret_cast<int32_t*>(ws + L.hnext); cp.hslot = reinterpret_cast<int32_t*>(ws + L.hslot); cp.tbits = L.tbits;
+      return tc::launch_gram_mh<MineEpi, 1, 2, true>(xm_bf16 + row_offset * L.Dp, xm_bf16, g, ep, grid, st, &cp, pdl);
+    }
     return tc::launch_gram<MineEpi>(xm_bf16 + row_offset * L.Dp, xm_bf16, mh, g, ep, grid, st, cg, pdl);
   }
   const float* X = L.xm_f32 ? xm_f32 : static_cast<const float*>(E_all);
@@ -811,19 +834,24 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   const bool vec = bh_vec8(E_all, D, dE_all);
 
   EFM_BH_STAGE(0, st);
-  EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));     // empty label table + empty chains
   const bool in_place = bh_mine_in_place(L, E_all, D, dtype);
   const __nv_bfloat16* xm_rows = in_place ? static_cast<const __nv_bfloat16*>(E_all) : xm_bf16;
+  const bool table_in_gram = bh_table_in_gram(L, B_local);
+  // empty label table + empty chains: by the prep kernel itself when it does not insert into the table, else a memset first
+  if (!table_in_gram) EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));
+  uint4* clr = table_in_gram ? reinterpret_cast<uint4*>(ws + L.clr_begin) : nullptr;
+  const long clr_n16 = table_in_gram ? (long)(L.clr_bytes / 16) : 0;
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, labels_all, B_all, (int)D, L.Dp, normalize,
                                                           L.use_tc ? 1 : 0, L.xm_f32 ? 1 : 0, row_offset, B_local, sq, nrm,
-                                                          lab, in_place ? nullptr : xm_bf16, xm_f32, kpos, kneg, nullptr, hkeys,
-                                                          hcnt, hmem, hhead, hnext, hslot, L.tbits);
+                                                          lab, in_place ? nullptr : xm_bf16, xm_f32, kpos, kneg, nullptr,
+                                                          table_in_gram ? nullptr : hkeys, hcnt, hmem, hhead, hnext, hslot, L.tbits,
+                                                          clr, clr_n16);
   });
   EFM_LAUNCH_CHECK("bh_prep");
   EFM_BH_STAGE(1, st);
   {
-    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, dtype, normalize, st, true);
+    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, dtype, normalize, st, true, table_in_gram);
     if (rc) return rc;
   }
   EFM_BH_STAGE(2, st);
@@ -888,7 +916,7 @@ extern "C" int efm_bh_backward(const void* E_all, long B_all, long row_offset, l
   EFM_BH_DISPATCH(dtype, vec, T, V, {
     bh_prep_kernel<T, V><<<grid_all, WARPS * 32, 0, st>>>((const T*)E_all, nullptr, B_all, (int)D, (int)D, normalize, 0, 0, 0, 0,
                                                           sq, nrm, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                          nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+                                                          nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0L);
   });
   EFM_LAUNCH_CHECK("bh_prep(stats)");
   if (B_local > 0) {
@@ -1020,7 +1048,7 @@ extern "C" int efm_bh_grad_rows(const void* E_all, long B_all, long D, int dtype
       bh_prep_kernel<T, V><<<(unsigned)cdiv(B_all, WARPS), WARPS * 32, 0, st>>>((const T*)E_all, nullptr, B_all, (int)D, (int)D, 1,
                                                                                  0, 0, 0, 0, sq, nrm, nullptr, nullptr, nullptr, nullptr,
                                                                                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                                 nullptr, nullptr, 0);
+                                                                                 nullptr, nullptr, 0, nullptr, 0L);
     });
     EFM_LAUNCH_CHECK("bh_prep(stats)");
   }
@@ -1048,8 +1076,10 @@ extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long 
   EFM_REQUIRE(E_all && workspace && aligned(workspace, 256), EFM_E_ARG, "efm_bh_mine: bad pointer");
   const BhLayout L = bh_layout(B_local, B_all, D, dtype, flags);
   EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_mine: workspace too small");
+  // same kernel variant as the step (the exchange warps re-register the rows in the label table: harmless, the next full
+  // step resets the table)
   return bh_launch_mining(L, E_all, static_cast<uint8_t*>(workspace), B_all, row_offset, B_local, D, dtype,
-                          (flags & EFM_BH_NORMALIZE) ? 1 : 0, static_cast<cudaStream_t>(stream));
+                          (flags & EFM_BH_NORMALIZE) ? 1 : 0, static_cast<cudaStream_t>(stream), false, bh_table_in_gram(L, B_local));
 }
 
 // ============================================================================================================
@@ -1225,14 +1255,14 @@ extern "C" int efm_bh_dist_fwd_bwd(const void* E_local, const int32_t* labels_lo
   const unsigned grid_loc = (unsigned)(B / WARPS);
 
   EFM_BH_STAGE(0, st);
-  EFM_CUDA(cudaMemsetAsync(ws + L.clr_begin, 0xFF, L.clr_bytes, st));
   if (!X.e_is_xm)                                                        // original rows next to the bf16 mining rows (stage B source)
     EFM_CUDA(cudaMemcpyAsync(buf + X.E + (size_t)row0 * D * es, E_local, (size_t)B * D * es, cudaMemcpyDeviceToDevice, st));
   // 1. local rows -> block `rank` of this step's buffer
   EFM_DISPATCH_DTYPE(dtype, T, {
     bh_prep_kernel<T, true><<<grid_loc, WARPS * 32, 0, st>>>((const T*)E_local, labels_local, B, (int)D, X.Dp, normalize, 1, 0, 0, B,
                                                              sq + row0, nrm + row0, lab + row0, xm + row0 * X.Dp, nullptr, kpos, kneg,
-                                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+                                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                                                             reinterpret_cast<uint4*>(ws + L.clr_begin), (long)(L.clr_bytes / 16));
   });
   EFM_LAUNCH_CHECK("bh_prep(local)");
   EFM_BH_STAGE(1, st);

@@ -75,8 +75,10 @@ struct GramParams {
 // push-style exchange costs 10-60 us while the links are busy and stalls the SM's TMA traffic for that long).
 constexpr int MAX_PEERS = 8;
 constexpr int MAX_XCHG_SEGS = 6;
-constexpr int COMM_WARPS = 2;            // exchange warps per CTA (COMM kernels): 2 x 32 lanes x 16 x 16 B = 16 KB of loads in flight per SM
-constexpr int PULL_DEPTH = 16;           // 16-byte loads in flight per lane (the copy is latency-bound: ~8 us per round trip under load)
+constexpr int COMM_WARPS = 2;            // exchange warps per CTA (COMM kernels): 2 x 32 lanes x 8 x 16 B = 8 KB of loads in flight per SM
+constexpr int PULL_DEPTH = 8;            // 16-byte loads in flight per lane.  Measured at 8 GPUs: 16 is SLOWER (Gram kernel 334 vs 252 us) --
+                                         // the remote loads (~8 us round trip under load) fill the SM's pending-request slots and the
+                                         // epilogue's own loads queue behind them
 struct XchgSeg { unsigned long long off; unsigned long long bytes; };   // offset of block 0 of an array inside a region; bytes per rank block
 struct CommParams {
   int world, rank;
