@@ -1,11 +1,13 @@
 """Multi-GPU forms of the two paths that have a real exchange step.
 
-* global batch-hard mining: all-gather of embeddings + labels (NCCL over NVLink on GPUs, gloo in CPU tests of
-  the host logic), every rank mines its B/P x B strip against the global batch; row extrema are complete per
-  rank, so mining needs no reduction.  Exact mode reduce-scatters dE_all so the result equals the single-GPU
-  loss on the concatenated batch WITHOUT a dense reduce-scatter (12 bytes per anchor are all-gathered instead and
-  every rank evaluates the terms that land on its own rows); detached mode (reference-faithful, negatives are
-  constants) needs no backward collective.
+* global batch-hard mining, fused (`PeerExchange`): one process per GPU, CUDA-IPC exchange regions, and ONE step per rank
+  with no NCCL call -- extra warps of the Gram + mining kernel copy the peers' rows over NVLink while the tensor pipeline
+  mines the blocks that have already arrived; the exact gradient fetches 12 bytes per anchor from the owners instead of
+  reduce-scattering a dense dE (csrc/bh.cu, efm_bh_dist_fwd_bwd).
+* global batch-hard mining, NCCL form (`global_batch_hard`): all-gather of embeddings + labels (gloo in the CPU tests of the
+  host logic), every rank mines its B/P x B strip against the global batch; row extrema are complete per rank, so mining
+  needs no reduction.  Exact mode all-gathers 12 bytes per anchor and every rank evaluates the terms that land on its own
+  rows; detached mode (reference-faithful, negatives are constants) needs no backward collective.
 * sharded gallery top-k: each rank owns a contiguous row shard, local top-k with global indices, all-gather of
   (score, idx) lists and a K-way merge on every rank.
 """
