@@ -529,3 +529,30 @@ def test_feature_export(P):
     out, fn = P.extract_features(net, None)
     assert P.format_feature_rows(fn) == O.format_feature_rows(fc.cpu().numpy())
     assert P.format_label_rows(torch.tensor([12.0, 3.0])) == O.format_label_rows(np.float32([12, 3]))
+
+
+def test_register_db_roundtrip(P, tmp_path):
+    """Register_DB_File / Select_Registed_Data (Feature.hpp:393-419,453-489) through the sqlite file: stored norms are the
+    exact sqrt(simd_dot), duplicates of rows already in the DB are skipped (sim >= 0.99999), and a gallery loaded from the
+    file answers like the in-memory one."""
+    F = P.formats
+    rng = np.random.default_rng(5)
+    G = rng.standard_normal((12, 342)).astype(np.float32)
+    paths = ["/faces/p%02d/im%d.jpg" % (i % 5, i) for i in range(12)]
+    db = str(tmp_path / "reg.db")
+    F.create_register_db(db)
+    assert F.register_db_file(db, paths[:8], dev(G[:8])) == 8
+    ids, names, G2, gn = F.select_registered(db, 342)
+    assert names == ["p%02d" % (i % 5) for i in range(8)] and np.array_equal(G2, G[:8])
+    assert np.array_equal(gn, np.array([np.sqrt(np.float32(O.simd_dot(g, g))) for g in G[:8]], dtype=np.float32))
+    # second call: rows 6, 7 are already registered -> skipped; 8..11 are new.  Duplicates WITHIN one call are not detected
+    # (AllMembers is loaded once before the loop, Feature.hpp:463-464)
+    batch = np.concatenate([G[6:12], G[11:12]])
+    assert F.register_db_file(db, paths[6:12] + [paths[11]], dev(batch)) == 5
+    gal, ids, names = F.load_gallery(db, 342)
+    assert gal.N == 13 and ids.tolist() == list(range(1, 14))
+    q = (G[9] + 0.01 * rng.standard_normal(342)).astype(np.float32)
+    idx, sim = gal.argmax(dev(q).reshape(1, -1), 0.5)
+    ref_idx, ref_sim = O.gallery_argmax(np.concatenate([G[:8], G[8:12], G[11:12]]), gal.gnorm.cpu().numpy(), q, 0.5)
+    assert int(idx[0]) == ref_idx == 9 and names[9] == "p04"
+    assert bits(sim)[0] == np.float32(ref_sim).view(np.int32)
