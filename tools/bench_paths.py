@@ -60,6 +60,34 @@ def efm_sites(dtype):
     out(path="mfm2_fwd", dtype=str(dtype), shape=[128, 198, 64, 64], ms=t * 1e3, gbs=b / t / 1e9, frac=b / t / 1e9 / PK["hbm_gbs"])
 
 
+def efm_sites_graph(dtype):
+    """All 30 EFM-3 sites of one LightCNN-29 forward (C1: N=128, 1x128x128 input) back to back as ONE CUDA graph launched
+    through the Python API calls (captured once): what the activation costs inside a network forward, without a host
+    round trip and an event pair per site.  Inputs are distinct tensors per site (4.8 GB of traffic per replay at fp32)."""
+    xs = []
+    for cnt, C, H, W in SITES:
+        for _ in range(cnt):
+            xs.append(torch.randn(128, C, H, W, device="cuda", dtype=dtype))
+    tot_b = sum(x.numel() * x.element_size() * (1 + 2 / 3) for x in xs)
+    for x in xs[:3]:
+        P.efm3(x)
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        for x in xs:
+            P.efm3(x)
+    torch.cuda.current_stream().wait_stream(st)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ys = [P.efm3(x) for x in xs]
+    t = timed(g.replay, iters=10)
+    out(path="efm3_fwd_all_30_sites_one_graph", dtype=str(dtype), launches=len(xs), ms=t * 1e3, bytes=tot_b, gbs=tot_b / t / 1e9,
+        frac=tot_b / t / 1e9 / PK["hbm_gbs"])
+    del ys, g, xs
+
+
 def rowops():
     B, D = 1 << 20, 256
     x = torch.randn(B, D, device="cuda")
@@ -105,6 +133,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["efm", "rowops", "allpairs", "gallery"]
     if "efm" in which:
         efm_sites(torch.float32); efm_sites(torch.bfloat16)
+    if "efmgraph" in which:
+        efm_sites_graph(torch.float32); efm_sites_graph(torch.bfloat16)
     if "rowops" in which:
         rowops()
     if "allpairs" in which:
