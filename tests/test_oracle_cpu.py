@@ -209,3 +209,29 @@ def test_lfw_protocol_shapes():
     assert acc.shape == (10,) and acc.mean() > 0.9
     folds = list(O.kfold_indices(103, 10))
     assert [len(t) for _, t in folds] == [11, 11, 11] + [10] * 7
+
+
+def test_mining_contract_cosine_equals_distance_of_normalised_rows():
+    """The tensor-core mining contract (oracle.batch_hard_triplet(mine_bf16=True)): for bf16 inputs the
+    cosine of the raw rows orders the candidates of an anchor exactly like the squared distance of the normalised rows, so
+    the mined indices equal those of the exact fp64 definition of SURVEY 8 a2' whenever the extrema are separated by more
+    than rounding noise (clustered data)."""
+    from util import clustered
+    for seed, (B, D) in enumerate([(256, 64), (512, 256), (300, 128)]):
+        E, y = clustered(B, D, seed=seed)
+        Eb = O.bf16_round(E.astype(np.float32)).astype(np.float64)          # what a bf16 tensor holds
+        a = O.batch_hard_triplet(Eb, y, 0.2, normalize=True, mine_bf16=True)
+        b = O.batch_hard_triplet(Eb, y, 0.2, normalize=True, mine_bf16=False)
+        assert np.array_equal(a["idx_p"], b["idx_p"]) and np.array_equal(a["idx_n"], b["idx_n"])
+        assert np.allclose(a["loss"], b["loss"], rtol=0, atol=1e-12)
+        # strip form (multi-GPU contract): rows [64, 192) against the whole batch
+        c = O.batch_hard_triplet(Eb[64:192], y[64:192], 0.2, normalize=True, E_all=Eb, labels_all=y, row_offset=64, mine_bf16=True)
+        assert np.array_equal(c["idx_p"], a["idx_p"][64:192]) and np.array_equal(c["idx_n"], a["idx_n"][64:192])
+    # duplicates: lowest index wins under both metrics
+    E, y = clustered(128, 64, seed=9)
+    E[100] = E[3]; E[77] = E[3]
+    Eb = O.bf16_round(E.astype(np.float32)).astype(np.float64)
+    a = O.batch_hard_triplet(Eb, y, 0.2, normalize=True, mine_bf16=True)
+    for i in range(128):
+        if a["idx_n"][i] in (77, 100):                                      # only allowed when row 3 itself is not a candidate
+            assert y[3] == y[i]
