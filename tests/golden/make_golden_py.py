@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref_python.npz by RUNNING THE REFERENCE'S OWN PYTHON FUNCTIONS in this container.
+
+The reference's scripts cannot run as a whole here (MXNet / TensorFlow / matplotlib are not installable), but three of
+its modules hold plain numpy / Python functions whose only obstacle is a module-level import of an absent package:
+
+  * draw_cos_dis_real.py            calc_counts, read_csv, calc_lines                      
+        obstacles: `import matplotlib.pyplot`, `np.float` (removed from numpy >= 1.24)
+  * feature_extraction/c_version/slice_celeb1m.py   read_fv, write2file, main()             
+  * feature_extraction/facenet_version/facenet.py   distance, calculate_accuracy, calculate_roc, calculate_val,
+        calculate_val_far                                                                    (LFW protocol)
+        obstacles: `import tensorflow`, `tensorflow.python.*`, `scipy.misc`
+
+This script puts EMPTY stand-in modules for exactly those absent packages into sys.modules (none of the functions
+above touches them), restores `np.float = float`, imports the reference modules from /root/reference UNMODIFIED, calls the
+functions on seeded inputs and stores inputs + outputs.  No reference source is copied.  The vectors pin the oracle /
+host restatements of these rows against the reference itself (tests/test_oracle_cpu.py, tests/test_formats_cpu.py,
+tests/test_verification_cpu.py).
+
+Run (needs /root/reference):  python tests/golden/make_golden_py.py
+"""
+import importlib.util
+import io
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+REF = os.environ.get("EFM_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def stub(name):
+    m = types.ModuleType(name)
+    sys.modules[name] = m
+    return m
+
+
+def load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tree not found at %s" % REF)
+    # ---- stand-ins for the absent packages (never called by the functions we run)
+    for n in ("matplotlib", "matplotlib.pyplot", "tensorflow", "tensorflow.python", "tensorflow.python.training",
+              "tensorflow.python.training.training", "tensorflow.python.platform", "tensorflow.python.platform.gfile"):
+        if n not in sys.modules:
+            stub(n)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["tensorflow.python.training"].training = sys.modules["tensorflow.python.training.training"]
+    sys.modules["tensorflow.python.platform"].gfile = sys.modules["tensorflow.python.platform.gfile"]
+    import scipy
+    if not hasattr(scipy, "misc"):
+        scipy.misc = stub("scipy.misc")
+    elif "scipy.misc" not in sys.modules:
+        sys.modules["scipy.misc"] = scipy.misc
+    if not hasattr(np, "float"):
+        np.float = float                                     # the shim SURVEY 8a5 names
+
+    out = {}
+    rng = np.random.default_rng(20261018)
+
+    # ------------------------------------------------------------------ a5: draw_cos_dis_real.py
+    dcr = load(os.path.join(REF, "draw_cos_dis_real.py"), "ref_draw_cos_dis_real")
+    n_rows = 1000
+    pos = np.clip(0.7 + 0.15 * rng.standard_normal(n_rows), -1, 1).astype(np.float32)
+    neg = np.clip(0.1 + 0.25 * rng.standard_normal(n_rows), -1, 1).astype(np.float32)
+    import csv
+    buf = io.StringIO()
+    w = csv.writer(buf, delimiter=" ")                      # how train_efm.py:252-255 writes the file
+    for a, b in zip(pos.tolist(), neg.tolist()):
+        w.writerow([a, b])
+    csv_text = buf.getvalue().replace("\r\n", "\n")
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            with open("cosine_similarity.csv", "w", newline="") as f:
+                f.write(csv_text)
+            for ep in (1, 5, 7):
+                p_list, n_list = dcr.read_csv(desire_epoch=ep)
+                out["a5_read_pos_ep%d" % ep] = np.array(p_list, dtype=np.float64)
+                out["a5_read_neg_ep%d" % ep] = np.array(n_list, dtype=np.float64)
+            p_list, n_list = dcr.read_csv(desire_epoch=5)
+        finally:
+            os.chdir(cwd)
+    out["a5_csv_text"] = np.frombuffer(csv_text.encode(), dtype=np.uint8)
+    cnt, edges = dcr.calc_counts(p_list)
+    out["a5_counts_pos"] = cnt; out["a5_edges_pos"] = edges
+    names = ["pos_line", "neg_line", "pos_cdf", "neg_cdf", "pos_bins", "neg_bins"]
+    for k, v in zip(names, dcr.calc_lines(pos_dis=p_list, neg_dis=n_list)):
+        out["a5_" + k] = np.asarray(v)
+
+    # ------------------------------------------------------------------ 8f-2: slice_celeb1m.py
+    sc = load(os.path.join(REF, "feature_extraction", "c_version", "slice_celeb1m.py"), "ref_slice_celeb1m")
+    ids = ["m.0%dx" % (i % 9) for i in range(60)]
+    rows = rng.standard_normal((60, 6)).astype(np.float32)
+    fv_text = "".join("{}, {}\n".format([float(v) for v in fv], ident) for fv, ident in zip(rows, ids))
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "feature_vector.txt"), "w") as f:
+            f.write(fv_text)
+        fv_id = sc.read_fv(os.path.join(td, "feature_vector.txt"))
+        out["fv_keys"] = np.array(list(fv_id.keys()))
+        out["fv_counts"] = np.array([len(fv_id[k]) for k in fv_id])
+        out["fv_first"] = np.array([fv_id[k][0] for k in fv_id], dtype=np.float64)
+        os.makedirs(os.path.join(td, "out"))
+        argv = sys.argv
+        sys.argv = ["slice_celeb1m.py", "--root2files", td, "--output_root", os.path.join(td, "out"), "--train_portion", "0.6"]
+        stdout = sys.stdout
+        sys.stdout = io.StringIO()
+        try:
+            sc.main()
+        finally:
+            sys.argv = argv
+            sys.stdout = stdout
+        for fn in ("train_img.csv", "train_id.txt", "test_img.csv", "test_id.txt"):
+            with open(os.path.join(td, "out", fn), "rb") as f:
+                out["fv_out_" + fn.replace(".", "_")] = np.frombuffer(f.read(), dtype=np.uint8)
+    out["fv_text"] = np.frombuffer(fv_text.encode(), dtype=np.uint8)
+    out["fv_train_portion"] = np.array([0.6])
+
+    # ------------------------------------------------------------------ 8f-4: facenet.py (LFW protocol)
+    fn = load(os.path.join(REF, "feature_extraction", "facenet_version", "facenet.py"), "ref_facenet")
+    P, D = 600, 32                                           # 600 pairs, 10 folds of 60 (LFW: 6000 pairs, 10 folds of 600)
+    cent = rng.standard_normal((P, D))
+    issame = (np.arange(P) % 2 == 0)
+    e1 = cent + 0.9 * rng.standard_normal((P, D))                      # hard enough for a non-trivial ROC
+    e2 = np.where(issame[:, None], cent + 0.9 * rng.standard_normal((P, D)), rng.standard_normal((P, D)))
+    e1 /= np.linalg.norm(e1, axis=1, keepdims=True); e2 /= np.linalg.norm(e2, axis=1, keepdims=True)
+    out["lfw_e1"] = e1; out["lfw_e2"] = e2; out["lfw_issame"] = issame
+    for metric in (0, 1):
+        out["lfw_dist_m%d" % metric] = fn.distance(e1, e2, metric)
+        thr = np.arange(0, 4, 0.01) if metric == 0 else np.arange(0, 1, 0.0025)
+        out["lfw_thr_m%d" % metric] = thr
+        for sm in (False, True):
+            tpr, fpr, acc = fn.calculate_roc(thr, e1, e2, issame, nrof_folds=10, distance_metric=metric, subtract_mean=sm)
+            tag = "m%d_sm%d" % (metric, int(sm))
+            out["lfw_tpr_" + tag] = tpr; out["lfw_fpr_" + tag] = fpr; out["lfw_acc_" + tag] = acc
+            try:
+                val, val_std, far = fn.calculate_val(thr, e1, e2, issame, 1e-2, nrof_folds=10, distance_metric=metric, subtract_mean=sm)
+                out["lfw_val_" + tag] = np.array([val, val_std, far])
+            except ValueError as e:
+                # scipy >= 1.10: interp1d(kind='slinear') refuses duplicate x, and the FAR curve of a threshold sweep always
+                # has duplicates -> the reference's calculate_val cannot run on this scipy; recorded, not pinned
+                out["lfw_val_error"] = np.frombuffer(("%s: %s" % (type(e).__name__, e)).encode(), dtype=np.uint8)
+    d0 = out["lfw_dist_m0"]
+    out["lfw_acc_at_1"] = np.array(fn.calculate_accuracy(1.0, d0, issame))
+    out["lfw_valfar_at_1"] = np.array(fn.calculate_val_far(1.0, d0, issame))
+
+    np.savez_compressed(os.path.join(OUT, "ref_python.npz"), **out)
+    print("wrote", os.path.join(OUT, "ref_python.npz"), "with", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -556,3 +556,21 @@ def test_register_db_roundtrip(P, tmp_path):
     ref_idx, ref_sim = O.gallery_argmax(np.concatenate([G[:8], G[8:12], G[11:12]]), gal.gnorm.cpu().numpy(), q, 0.5)
     assert int(idx[0]) == ref_idx == 9 and names[9] == "p04"
     assert bits(sim)[0] == np.float32(ref_sim).view(np.int32)
+
+
+def test_lfw_pair_distances_on_device(P):
+    """verification.pair_distances (GPU operators) == facenet.distance on the gathered rows, both metrics, and the ROC built
+    from them equals the host protocol on the same embeddings (C4-shaped: index pairs into one embedding matrix)."""
+    import os
+    V = P.verification
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python.npz"))
+    e1, e2, same = g["lfw_e1"].astype(np.float32), g["lfw_e2"].astype(np.float32), g["lfw_issame"]
+    E = np.concatenate([e1, e2]); n = e1.shape[0]
+    ia, ib = np.arange(n, dtype=np.int32), np.arange(n, 2 * n, dtype=np.int32)
+    for m, tol in ((0, 1e-5), (1, 1e-4)):
+        d = V.pair_distances(dev(E), ia, ib, distance_metric=m)
+        ref = V.distance(e1.astype(np.float64), e2.astype(np.float64), m)
+        assert np.abs(d - ref).max() < tol * max(1.0, np.abs(ref).max())
+    d0 = V.pair_distances(dev(E), ia, ib, distance_metric=0)
+    acc_dev = V.calculate_accuracy(1.0, d0, same)
+    assert abs(acc_dev[2] - float(g["lfw_acc_at_1"][2])) <= 2.0 / n          # at most a borderline pair or two flips
