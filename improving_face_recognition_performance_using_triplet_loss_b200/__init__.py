@@ -10,7 +10,8 @@ from .cosine import (calc_counts, calc_lines, cosine_allpairs, cosine_dist, cosi
                      read_csv, write_cosine_csv)
 from .features import (acc, extract_features, format_feature_rows, format_label_rows, write_feature_csv,
                        write_label_csv)
-from . import formats, verification
+from . import batches, formats, verification
+from .batches import TripletPairIter, define_pos, pk_batches
 from .gallery import (Compare_Face_DB, Compare_Face_From_DB, Compare_Face_Person, Gallery, merge_topk, simd_dot)
 from .loss import (BatchHardTripletLoss, TripletLoss, batch_hard_backward, batch_hard_grad_rows, batch_hard_triplet,
                    sample_negatives, triplet_loss)
@@ -22,5 +23,6 @@ __all__ = [
     "cosine_pairs", "cosine_pairs_indexed", "cosine_allpairs", "write_cosine_csv", "read_csv", "calc_counts",
     "calc_lines", "Gallery", "merge_topk", "simd_dot", "Compare_Face_From_DB", "Compare_Face_Person",
     "Compare_Face_DB", "extract_features", "acc", "format_feature_rows", "format_label_rows", "write_feature_csv",
-    "write_label_csv", "formats", "verification", "EfmError", "last_error",
+    "write_label_csv", "formats", "verification", "batches", "TripletPairIter", "define_pos", "pk_batches", "EfmError",
+    "last_error",
 ]

@@ -10,6 +10,8 @@ its modules hold plain numpy / Python functions whose only obstacle is a module-
   * feature_extraction/facenet_version/facenet.py   distance, calculate_accuracy, calculate_roc, calculate_val,
         calculate_val_far                                                                    (LFW protocol)
         obstacles: `import tensorflow`, `tensorflow.python.*`, `scipy.misc`
+  * train_efm.py                    define_pos, Batch, DataIter (the 2B-row batch layout)  
+        obstacles: `import mxnet` (used here only as the array CARRIER), module-level training code after the definitions
 
 This script puts EMPTY stand-in modules for exactly those absent packages into sys.modules (none of the functions
 above touches them), restores `np.float = float`, imports the reference modules from /root/reference UNMODIFIED, calls the
@@ -153,6 +155,81 @@ def main():
     d0 = out["lfw_dist_m0"]
     out["lfw_acc_at_1"] = np.array(fn.calculate_accuracy(1.0, d0, issame))
     out["lfw_valfar_at_1"] = np.array(fn.calculate_val_far(1.0, d0, issame))
+
+    # ------------------------------------------------------------------ 8f-1: define_pos + DataIter (train_efm.py:37-114)
+    # train_efm.py trains at module level, so only its definitions (everything before the "Data & Parameter setting" block)
+    # are executed, read from the reference tree at run time, against a CARRIER-ONLY stand-in for mxnet: an NDArray that
+    # wraps numpy and offers the four carrier methods these definitions use (indexing, asnumpy, asscalar, shape) -- no
+    # arithmetic of the reference goes through it.
+    class FakeND(object):
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=np.float32)
+        def __getitem__(self, i):
+            return FakeND(self.a[i])
+        def asnumpy(self):
+            return self.a
+        def asscalar(self):
+            return self.a.reshape(-1)[0]
+        @property
+        def shape(self):
+            return self.a.shape
+        def __len__(self):
+            return len(self.a)
+    mx = stub("mxnet")
+    mx.nd = stub("mxnet.nd"); mx.nd.array = lambda x: FakeND(np.array([e.a if isinstance(e, FakeND) else e for e in x]) if isinstance(x, list) else x)
+    mx.io = stub("mxnet.io")
+    class _DataIterBase(object):
+        def __init__(self, *a, **k):
+            pass
+    mx.io.DataIter = _DataIterBase
+    for n in ("mxnet.autograd", "mxnet.gluon", "mxnet.init", "mxnet.gluon.nn", "lightcnn", "gluoncv"):
+        stub(n)
+    mx.autograd = sys.modules["mxnet.autograd"]; mx.gluon = sys.modules["mxnet.gluon"]; mx.init = sys.modules["mxnet.init"]
+    mx.gluon.nn = sys.modules["mxnet.gluon.nn"]
+    src = open(os.path.join(REF, "train_efm.py")).read()
+    cut = src.index('""" Data & Parameter setting """')
+    ns = {"__name__": "ref_train_efm_defs"}
+    exec(compile(src[:cut], os.path.join(REF, "train_efm.py"), "exec"), ns)
+    Bsz, nb = 4, 6
+    lab = rng.integers(0, 7, Bsz * nb).astype(np.float32)
+    imgs = rng.random((Bsz * nb, 1, 2, 3)).astype(np.float32)
+    class _B(object):
+        def __init__(self, d, l):
+            self.data = [FakeND(d)]; self.label = [FakeND(l)]
+    batches = [_B(imgs[i * Bsz:(i + 1) * Bsz], lab[i * Bsz:(i + 1) * Bsz]) for i in range(nb)]
+    pos_img = ns["define_pos"](batches, nb, Bsz)
+    out["f1_imgs"] = imgs; out["f1_labels"] = lab
+    out["f1_pos_keys"] = np.array(list(pos_img.keys()), dtype=np.int64)
+    out["f1_pos_imgs"] = np.stack([pos_img[k].asnumpy() for k in pos_img])
+    it = ns["DataIter"](batches, nb, pos_img, Bsz, (Bsz, 1, 2, 3))
+    got_d, got_l = [], []
+    for b in it:
+        got_d.append(b.data[0].asnumpy()); got_l.append(b.label[0].asnumpy())
+    out["f1_batches_data"] = np.stack(got_d); out["f1_batches_label"] = np.stack(got_l)
+
+    # ------------------------------------------------------------------ a2: negative selection (train_efm.py:234-238, :268-272)
+    # The rejection-sampling loops live inline in the training / validation loops.  Their source lines are read from the
+    # reference tree at run time, dedented and executed with carrier stand-ins: `label` a FakeND, `fc` a FakeND whose row j
+    # holds the number j (so the appended rows reveal the drawn indices), Python's module-level `random` seeded.
+    import random
+    import textwrap
+    lines = src.splitlines()
+    def loop_after(marker_line_no):
+        k = next(i for i in range(marker_line_no, len(lines)) if lines[i].strip().startswith("for i in range(batch_size):"))
+        end = next(i for i in range(k + 1, len(lines)) if "neg.append" in lines[i])
+        return textwrap.dedent("\n".join(lines[k:end + 1]))
+    train_loop = loop_after(next(i for i, l in enumerate(lines) if '""" training loop """' in l))
+    val_loop = loop_after(next(i for i, l in enumerate(lines) if '""" validation loop """' in l))
+    assert "batch_size - 1" in train_loop and "batch_size*2 - 1" in val_loop     # pools: anchor half (train), both halves (val)
+    Bn = 16
+    lab2 = np.concatenate([rng.integers(0, 5, Bn)] * 2).astype(np.float32)    # duplicated halves like the loader emits
+    out["a2_labels"] = lab2
+    for tag, code in (("train", train_loop), ("val", val_loop)):
+        for seed in (0, 1, 12345):
+            random.seed(seed)
+            env = {"random": random, "batch_size": Bn, "label": FakeND(lab2), "fc": FakeND(np.arange(2 * Bn).reshape(-1, 1)), "neg": []}
+            exec(code, env)
+            out["a2_%s_seed%d" % (tag, seed)] = np.array([int(r[0]) for r in env["neg"]], dtype=np.int64)
 
     np.savez_compressed(os.path.join(OUT, "ref_python.npz"), **out)
     print("wrote", os.path.join(OUT, "ref_python.npz"), "with", len(out), "arrays")
