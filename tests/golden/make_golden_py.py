@@ -231,6 +231,34 @@ def main():
             exec(code, env)
             out["a2_%s_seed%d" % (tag, seed)] = np.array([int(r[0]) for r in env["neg"]], dtype=np.int64)
 
+    # ------------------------------------------------------------------ a7: feature / label export text (extract_feacture_v2.py:67-79)
+    # The two `with open(...)` blocks of the training loop, read from the reference tree and executed in a scratch directory.
+    # What is pinned is the TEXT FORMAT ('{},' per element with a trailing comma, numpy-float32 label repr); the normalisation
+    # itself runs through a numpy-float32 stand-in for `mx.nd.norm` / NDArray division and its result is stored next to
+    # the text, so the test formats exactly these values.
+    class FakeND2(FakeND):
+        def __truediv__(self, o):
+            return FakeND2(self.a / (o.a if isinstance(o, FakeND) else o))
+        def __getitem__(self, i):
+            return FakeND2(self.a[i])
+    mx.nd.norm = lambda x: FakeND2(np.sqrt(np.sum(np.square(x.a), dtype=np.float32), dtype=np.float32).reshape(1))
+    esrc = open(os.path.join(REF, "extract_feacture_v2.py")).read().splitlines()
+    k0 = next(i for i, l in enumerate(esrc) if '""" save feature vectors """' in l)
+    k1 = next(i for i in range(k0, len(esrc)) if esrc[i].strip().startswith("print("))
+    block = textwrap.dedent("\n".join(esrc[k0:k1]))
+    fc = rng.standard_normal((5, 7)).astype(np.float32)
+    labv = np.array([12, 0, 3, 78578, 7], dtype=np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            exec(block, {"mx": mx, "fc": FakeND2(fc), "label": FakeND2(labv), "batch_size": 5})
+            out["a7_feature_csv"] = np.frombuffer(open("feature_vector_train.csv", "rb").read(), dtype=np.uint8)
+            out["a7_label_csv"] = np.frombuffer(open("label_train.csv", "rb").read(), dtype=np.uint8)
+        finally:
+            os.chdir(cwd)
+    out["a7_fc_normalised"] = np.stack([fc[v] / np.sqrt(np.sum(np.square(fc[v]), dtype=np.float32), dtype=np.float32) for v in range(5)])
+    out["a7_labels"] = labv
+
     np.savez_compressed(os.path.join(OUT, "ref_python.npz"), **out)
     print("wrote", os.path.join(OUT, "ref_python.npz"), "with", len(out), "arrays")
 
