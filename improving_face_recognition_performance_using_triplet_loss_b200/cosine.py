@@ -68,14 +68,16 @@ def cosine_allpairs(A: torch.Tensor, B: torch.Tensor | None = None) -> torch.Ten
 
 
 def write_cosine_csv(path, pos, neg, mode="a+"):
-    """cosine_similarity.csv rows "pos neg" (train_efm.py:250-255: csv.writer(delimiter=' '), one host copy)."""
+    """cosine_similarity.csv rows "pos neg" exactly as train_efm.py:250-255 writes them: csv.writer(delimiter=' ') over
+    `asscalar()` values, which are numpy.float32 scalars -- csv stringifies those with str(), i.e. the SHORTEST float32
+    repr ('0.70710677', not the 17-digit repr of the widened double), '\r\n' line ends.  One host copy per call."""
     import csv
-    p = pos.detach().float().cpu().tolist() if isinstance(pos, torch.Tensor) else [float(v) for v in pos]
-    n = neg.detach().float().cpu().tolist() if isinstance(neg, torch.Tensor) else [float(v) for v in neg]
+    p = pos.detach().float().cpu().numpy().reshape(-1) if isinstance(pos, torch.Tensor) else np.asarray(pos, dtype=np.float32).reshape(-1)
+    n = neg.detach().float().cpu().numpy().reshape(-1) if isinstance(neg, torch.Tensor) else np.asarray(neg, dtype=np.float32).reshape(-1)
     with open(path, mode, newline="") as f:
         w = csv.writer(f, delimiter=" ")
         for a, b in zip(p, n):
-            w.writerow([a, b])
+            w.writerow([np.float32(a), np.float32(b)])
 
 
 # ---- draw_cos_dis_real.py statistics (plotting itself is out of scope) -----------------------------------

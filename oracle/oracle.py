@@ -395,11 +395,12 @@ def cosine_allpairs(A, Bm, dtype=F32):
 
 
 def format_cosine_csv(pos, neg):
-    """csv.writer(delimiter=' ').writerow([pos.asscalar(), neg.asscalar()]) per row:
-    repr of the Python float holding the fp32 value, '\\r\\n' line terminator (csv default)."""
+    """csv.writer(delimiter=' ').writerow([pos.asscalar(), neg.asscalar()]) per row (train_efm.py:250-255): asscalar()
+    yields numpy.float32 scalars, which csv stringifies with str() -> shortest float32 repr; '\r\n' line terminator
+    (csv default).  Pinned against the reference block itself (tests/golden/ref_python.npz)."""
     rows = []
     for p, n in zip(np.asarray(pos, dtype=F32).reshape(-1), np.asarray(neg, dtype=F32).reshape(-1)):
-        rows.append("{} {}\r\n".format(repr(float(p)), repr(float(n))))
+        rows.append("{} {}\r\n".format(str(F32(p)), str(F32(n))))
     return "".join(rows)
 
 

@@ -259,6 +259,25 @@ def main():
     out["a7_fc_normalised"] = np.stack([fc[v] / np.sqrt(np.sum(np.square(fc[v]), dtype=np.float32), dtype=np.float32) for v in range(5)])
     out["a7_labels"] = labv
 
+    # ------------------------------------------------------------------ a4: cosine_similarity.csv rows (train_efm.py:250-255)
+    # The block that appends "pos neg" rows, read from the reference tree; `cosine_dist` is replaced by a stand-in that
+    # returns the given similarities as (1,) carriers whose asscalar() is a numpy.float32 -- as MXNet's is, which is what
+    # decides the text (csv.writer stringifies a numpy.float32 with str(): shortest float32 repr).
+    k0 = next(i for i, l in enumerate(lines) if "save positive distance and negative distance to csv" in l)
+    k1 = next(i for i in range(k0, len(lines)) if "csvwriter.writerow" in lines[i])
+    block = textwrap.dedent("\n".join(lines[k0:k1 + 1]))
+    pd_ = np.array([0.70710678, 1.0, -0.1, 1e-8, 0.33333334], dtype=np.float32)
+    nd_ = np.array([-0.25, 0.5, 0.123456789, -1.0, 3e-5], dtype=np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            exec(block, {"csv": csv, "batch_size": 5, "anc": None, "pos": None, "neg": None,
+                         "cosine_dist": lambda a, p, n, b: ([FakeND(pd_[i:i + 1]) for i in range(b)], [FakeND(nd_[i:i + 1]) for i in range(b)])})
+            out["a4_csv_bytes"] = np.frombuffer(open("cosine_similarity.csv", "rb").read(), dtype=np.uint8)
+        finally:
+            os.chdir(cwd)
+    out["a4_pos"] = pd_; out["a4_neg"] = nd_
+
     np.savez_compressed(os.path.join(OUT, "ref_python.npz"), **out)
     print("wrote", os.path.join(OUT, "ref_python.npz"), "with", len(out), "arrays")
 
