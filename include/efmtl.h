@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EFM_ABI_VERSION 1
+#define EFM_ABI_VERSION 2   /* 2: multi-GPU fused step (efm_bh_dist_fwd_bwd, efm_xchg_*, efm_ipc_*), efm_bh_profile_events */
 
 /* dtype codes */
 #define EFM_F32  0

@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(L):
 
 
 def test_abi_version_and_error_string(L):
-    assert L.lib.efm_abi_version() == 1
+    assert L.lib.efm_abi_version() == 2
     rc = L.lib.efm_act_fwd(7, None, None, 1, 3, 1, 0, None)            # bad mode: rejected before any CUDA call
     assert rc == -1 and "mode" in L.last_error()
     rc = L.lib.efm_act_fwd(3, None, None, 1, 4, 1, 0, None)            # C % 3 != 0
