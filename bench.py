@@ -500,7 +500,7 @@ def run_ours(args):
                     "how": "public API (%s), pinned host E+labels -> device, loss+idx_p+idx_n -> pinned host every step, "
                            "wall clock" % ("PeerExchange.step()" if fused else "batch_hard_triplet()")},
             "gpu_launches": len(launches_per_step) * args.steps,   # kernels of the timed steps (the roofline / e2e loops launch theirs on top)
-            "launches_per_step": launches_per_step, "memsets_per_step": 1,
+            "launches_per_step": launches_per_step, "memsets_per_step": 0,   # table / chain reset is folded into bh_prep
             "step_breakdown_us": breakdown,   # CUDA events between the launches of one step (each interval includes its launch gap)
             "clocks": clocks,
             "pairs_per_s": (float(B) * G * world) / (t_step * 1e-3),
