@@ -384,6 +384,7 @@ def run_ours(args):
         for e in free:
             e.record(main)
         keep = [None, None]
+        bhs = None if (fused or world > 1) else P.BatchHardStep(B, DIM, torch.bfloat16, MARGIN, normalize=True, device=dev)
         for i in range(steps):
             b = i & 1
             with torch.cuda.stream(copy):
@@ -393,6 +394,8 @@ def run_ours(args):
             main.wait_event(ready[b])
             if fused:
                 l, ip, inn, dE = px.step(Ed[b], yd[b], MARGIN, normalize=True)
+            elif bhs is not None:
+                l, ip, inn, dE = bhs.step(Ed[b], yd[b])               # public API, preallocated form: one library call
             else:
                 if world > 1:
                     Ea = D.all_gather_rows(Ed[b]); ya = D.all_gather_rows(yd[b])
@@ -498,7 +501,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(B * 12), "ms_per_step": t_e2e * 1e3,
                     "ms_per_step_serial": t_e2e_serial * 1e3, "mode": e2e_mode,
                     "how": "public API (%s), pinned host E+labels -> device, loss+idx_p+idx_n -> pinned host every step, "
-                           "wall clock" % ("PeerExchange.step()" if fused else "batch_hard_triplet()")},
+                           "wall clock" % ("PeerExchange.step()" if fused else "batch_hard_triplet() serial / BatchHardStep.step() pipelined")},
             "gpu_launches": len(launches_per_step) * args.steps,   # kernels of the timed steps (the roofline / e2e loops launch theirs on top)
             "launches_per_step": launches_per_step, "memsets_per_step": 0,   # table / chain reset is folded into bh_prep
             "step_breakdown_us": breakdown,   # CUDA events between the launches of one step (each interval includes its launch gap)

@@ -13,12 +13,12 @@ from .features import (acc, extract_features, format_feature_rows, format_label_
 from . import batches, formats, verification
 from .batches import TripletPairIter, define_pos, pk_batches
 from .gallery import (Compare_Face_DB, Compare_Face_From_DB, Compare_Face_Person, Gallery, merge_topk, simd_dot)
-from .loss import (BatchHardTripletLoss, TripletLoss, batch_hard_backward, batch_hard_grad_rows, batch_hard_triplet,
+from .loss import (BatchHardStep, BatchHardTripletLoss, TripletLoss, batch_hard_backward, batch_hard_grad_rows, batch_hard_triplet,
                    sample_negatives, triplet_loss)
 from .norm import frob_normalize, l2_normalize, norm, row_norms
 
 __all__ = [
-    "EFM", "efm", "efm3", "mfm2", "TripletLoss", "triplet_loss", "BatchHardTripletLoss", "batch_hard_triplet",
+    "EFM", "efm", "efm3", "mfm2", "TripletLoss", "triplet_loss", "BatchHardTripletLoss", "BatchHardStep", "batch_hard_triplet",
     "batch_hard_backward", "batch_hard_grad_rows", "sample_negatives", "norm", "l2_normalize", "frob_normalize", "row_norms", "cosine_dist",
     "cosine_pairs", "cosine_pairs_indexed", "cosine_allpairs", "write_cosine_csv", "read_csv", "calc_counts",
     "calc_lines", "Gallery", "merge_topk", "simd_dot", "Compare_Face_From_DB", "Compare_Face_Person",

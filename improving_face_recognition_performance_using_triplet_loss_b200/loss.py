@@ -150,6 +150,42 @@ def batch_hard_triplet(E_all, labels_all, margin, *, normalize=True, row_offset=
     return loss, idx_p, idx_n, dE
 
 
+class BatchHardStep:
+    """The fused batch-hard step for a FIXED shape with everything allocated once (outputs, workspace): `step()` is one
+    library call and a handful of Python operations -- what a training loop that runs the same (B, D) every iteration
+    wants (the functional `batch_hard_triplet` spends tens of microseconds per call on allocations and checks, about as
+    long as the 63 us GPU step itself).  The returned tensors are REUSED by the next call of the same object."""
+
+    def __init__(self, B_all, D, dtype, margin, *, normalize=True, row_offset=0, num_local=None, want_grad=True,
+                 detach_gathered=False, mine_bf16=None, device=None):
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.B_all, self.D, self.dtype, self.device = int(B_all), int(D), dtype, dev
+        self.B = self.B_all - int(row_offset) if num_local is None else int(num_local)
+        self.row_offset, self.margin = int(row_offset), float(margin)
+        self.dt = L._DTYPES[dtype]
+        self.flags = _bh_flags(normalize, detach_gathered, bool(mine_bf16))
+        self.ws = L.workspace(L.lib.efm_bh_workspace_bytes(self.B, self.B_all, self.D, self.dt, self.flags), dev)
+        self.loss = torch.empty(self.B, dtype=torch.float32, device=dev)
+        self.idx_p = torch.empty(self.B, dtype=torch.int32, device=dev)
+        self.idx_n = torch.empty(self.B, dtype=torch.int32, device=dev)
+        self.dE = torch.empty((self.B_all, self.D), dtype=torch.float32, device=dev) if want_grad else None
+        self._out = (L.ptr(self.loss), L.ptr(self.idx_p), L.ptr(self.idx_n), L.ptr(self.dE), L.ptr(self.ws), self.ws.numel())
+
+    def step(self, E_all, labels_all, head_grad=None):
+        """E_all: (B_all, D) contiguous CUDA tensor of the construction dtype; labels_all: (B_all,) int32 CUDA tensor.
+        Enqueues the step on the current stream of E_all's device (which must be the current device) and returns
+        (loss, idx_p, idx_n, dE) -- the object's own buffers."""
+        if E_all.dtype != self.dtype or E_all.shape != (self.B_all, self.D) or not E_all.is_contiguous() or not E_all.is_cuda:
+            raise ValueError("E_all must be a contiguous (%d, %d) %s CUDA tensor" % (self.B_all, self.D, self.dtype))
+        if labels_all.dtype != torch.int32 or labels_all.numel() != self.B_all or not labels_all.is_contiguous():
+            raise ValueError("labels_all must be a contiguous (%d,) int32 tensor" % self.B_all)
+        o = self._out
+        L.check(L.lib.efm_bh_triplet_fwd_bwd(E_all.data_ptr(), labels_all.data_ptr(), self.B_all, self.row_offset, self.B, self.D,
+                                             self.dt, self.margin, L.ptr(head_grad), self.flags, o[0], o[1], o[2], o[3], o[4], o[5],
+                                             torch.cuda.current_stream(self.device).cuda_stream))
+        return self.loss, self.idx_p, self.idx_n, self.dE
+
+
 def batch_hard_backward(E_all, idx_p, idx_n, margin, head_grad, *, normalize=True, row_offset=0, detach_gathered=False):
     """Gradient for given mined indices and per-anchor head gradient -> dE_all (B_all, D) fp32."""
     L.require_cuda(E_all)

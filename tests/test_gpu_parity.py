@@ -574,3 +574,23 @@ def test_lfw_pair_distances_on_device(P):
     d0 = V.pair_distances(dev(E), ia, ib, distance_metric=0)
     acc_dev = V.calculate_accuracy(1.0, d0, same)
     assert abs(acc_dev[2] - float(g["lfw_acc_at_1"][2])) <= 2.0 / n          # at most a borderline pair or two flips
+
+
+def test_batch_hard_step_object_equals_functional_call(P):
+    """BatchHardStep (everything allocated once, one library call per step) == batch_hard_triplet, over several batches,
+    with and without a head gradient; its buffers are reused."""
+    B, D = 512, 128
+    st = P.BatchHardStep(B, D, torch.bfloat16, 1.9)
+    for s in range(3):
+        E, y = clustered(B, D, seed=70 + s)
+        Et, yt = dev(E, torch.bfloat16), dev(y)
+        hg = torch.linspace(0.5, 1.5, B).cuda() if s == 2 else None
+        ref = P.batch_hard_triplet(Et, yt, 1.9, head_grad=hg)
+        l, ip, inn, dE = st.step(Et, yt, head_grad=hg)
+        assert torch.equal(l, ref[0]) and torch.equal(ip, ref[1]) and torch.equal(inn, ref[2])
+        assert rel_err(dE.cpu().numpy(), ref[3].cpu().numpy()) < 1e-5
+        assert l.data_ptr() == st.loss.data_ptr()
+    with pytest.raises(ValueError):
+        st.step(dev(E, torch.float32), yt)
+    with pytest.raises(ValueError):
+        st.step(Et, yt.long())
