@@ -108,6 +108,19 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs must use all host cores (BLAS pools are sized when
+    numpy loads, so the limit is lifted at run time).  Returns the thread count of the largest BLAS / OpenMP pool."""
+    n = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        pools = threadpoolctl.threadpool_info()
+        return max([p.get("num_threads", 1) for p in pools] + [1])
+    except Exception:  # noqa: BLE001
+        return n
+
+
 def cpu_port_step(E, y):
     import oracle as O
     return O.batch_hard_triplet_fast(E, y, MARGIN, normalize=True)
@@ -158,7 +171,7 @@ def run_reference(args):
     name, G, scaling = workload_of(args, world)
     S = max(64, B_LOCAL // world) if name != "c3" and name != "c3-nccl" else 1024
     E, y = make_batch(G, DIM, 0)
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads()
 
     def one():
         return O.batch_hard_strip_fast(E, y, 0, S, MARGIN, normalize=True)
@@ -512,8 +525,9 @@ def run_ours(args):
             line["c3_single_gpu_ms_per_step"] = t_single
             line["speedup_vs_single_gpu"] = t_single / t_step
         if world == 1 and name == "c2" and not args.no_cpu:
+            cores = use_all_host_threads()
             best, n = time_cpu(E_np, y_np)
-            line["cpu_baseline"] = {"value": B / best, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            line["cpu_baseline"] = {"value": B / best, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "full C2 batch, best of %d steps (oracle numpy/BLAS port: Gram + mining + hinge "
                                               "+ scatter + normalise-backward)" % n, "ms_per_step": best * 1e3}
         print(json.dumps(line), flush=True)
