@@ -735,7 +735,9 @@ static bool bh_table_in_gram(const BhLayout& L, long B_local) {
 }
 
 static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, long B_all, long row_offset, long B_local,
-                            long D, int dtype, int normalize, cudaStream_t st, bool pdl = false, bool build_table = false) {
+                            long D, int dtype, int normalize, cudaStream_t st, bool pdl = false, int build_table = 0) {
+  // build_table: 0 = plain kernel, 1 = variant with the extra warps, which build the label table, 2 = same variant, table
+  // left alone (efm_bh_mine: re-registering the rows of a populated table would corrupt its overflow chains)
   auto* kpos = reinterpret_cast<unsigned long long*>(ws + L.kpos);
   auto* kneg = reinterpret_cast<unsigned long long*>(ws + L.kneg);
   float* sq = reinterpret_cast<float*>(ws + L.sq);
@@ -758,7 +760,7 @@ static int bh_launch_mining(const BhLayout& L, const void* E_all, uint8_t* ws, l
       EFM_REQUIRE(g.stages >= 1, EFM_E_UNSUPPORTED, "gram: K = %d leaves no shared memory for the B pipeline", g.nk * tc::BK);
       tc::CommParams cp{};
       cp.world = 1;
-      cp.tab_lab = lab; cp.tab_rows = B_all;
+      cp.tab_lab = build_table == 1 ? lab : nullptr; cp.tab_rows = B_all;
       cp.hkeys = reinterpret_cast<unsigned long long*>(ws + L.hkeys); cp.hcnt = reinterpret_cast<int32_t*>(ws + L.hcnt);
       cp.hmem = reinterpret_cast<int32_t*>(ws + L.hmem); cp.hhead = reinterpret_cast<int32_t*>(ws + L.hhead);
       cp.hnext = reinterpret_cast<int32_t*>(ws + L.hnext); cp.hslot = reinterpret_cast<int32_t*>(ws + L.hslot); cp.tbits = L.tbits;
@@ -851,7 +853,7 @@ extern "C" int efm_bh_triplet_fwd_bwd(const void* E_all, const int32_t* labels_a
   EFM_LAUNCH_CHECK("bh_prep");
   EFM_BH_STAGE(1, st);
   {
-    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, dtype, normalize, st, true, table_in_gram);
+    int rc = bh_launch_mining(L, E_all, ws, B_all, row_offset, B_local, D, dtype, normalize, st, true, table_in_gram ? 1 : 0);
     if (rc) return rc;
   }
   EFM_BH_STAGE(2, st);
@@ -1076,10 +1078,10 @@ extern "C" int efm_bh_mine(const void* E_all, long B_all, long row_offset, long 
   EFM_REQUIRE(E_all && workspace && aligned(workspace, 256), EFM_E_ARG, "efm_bh_mine: bad pointer");
   const BhLayout L = bh_layout(B_local, B_all, D, dtype, flags);
   EFM_REQUIRE(ws_bytes >= L.total, EFM_E_WORKSPACE, "efm_bh_mine: workspace too small");
-  // same kernel variant as the step (the exchange warps re-register the rows in the label table: harmless, the next full
-  // step resets the table)
+  // same kernel variant as the step; its extra warps leave the (already populated) label table alone
   return bh_launch_mining(L, E_all, static_cast<uint8_t*>(workspace), B_all, row_offset, B_local, D, dtype,
-                          (flags & EFM_BH_NORMALIZE) ? 1 : 0, static_cast<cudaStream_t>(stream), false, bh_table_in_gram(L, B_local));
+                          (flags & EFM_BH_NORMALIZE) ? 1 : 0, static_cast<cudaStream_t>(stream), false,
+                          bh_table_in_gram(L, B_local) ? 2 : 0);
 }
 
 // ============================================================================================================
