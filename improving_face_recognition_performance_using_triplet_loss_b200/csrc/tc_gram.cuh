@@ -742,10 +742,12 @@ int launch_gram_mh(const void* A, const void* B, GramParams g, const typename Ep
   if (g.phases < 1) g.phases = 1;
   const size_t smem = 1024 + (size_t)g.nk * Shape<MH>::A_KB_BYTES + (size_t)g.stages * (Shape<MH>::B_ST_BYTES / CG) + 256 +
                       Epi::SMEM_PER_WARP * EPI_WARPS;
-  static bool attr_done = false;                                     // per instantiation
-  if (!attr_done) {
+  static bool attr_done[64] = {};                                    // per instantiation and per device (the attribute is per device)
+  int dev = 0;
+  EFM_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     EFM_CUDA(cudaFuncSetAttribute(gram_kernel<Epi, MH, CG, COMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   CommParams none{};
   const CommParams& c = cp ? *cp : none;

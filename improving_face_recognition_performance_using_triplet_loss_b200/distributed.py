@@ -152,6 +152,12 @@ class PeerExchange:
                                               L.stream()))
         return loss, idx_p, idx_n, dE
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def close(self):
         """Collective: every rank must call it (peers may still be reading this rank's region otherwise)."""
         if self._own is None:
